@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- FCD height-map throughput on B200 (BASELINE.json metric: height-map frames/s
+at 2048^2; achieved HBM GB/s).
+
+    python bench.py --gpus 1 --steps K --warmup W              # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W      # reference CPU algorithm (oracle port)
+    torchrun ... bench.py --gpus N ...                         # one rank per GPU, frame-sharded
+
+A "step" is one pass of the hot path over one batch of synthetic frames (BASELINE.json
+configs[1]: 1000 frames of 2048x2048 float32 with one reference, per GPU).  `value` is
+whole-job frames/s with inputs already resident in HBM; `e2e` is the same metric through the
+public API with HOST (pinned) buffers, host<->device copies inside the timed region.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "trapped-modes-ltg_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+SEED = 20251018
+METRIC = "height_map_frames_per_s_2048x2048"
+
+
+# --------------------------------------------------------------------------------------
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=2048)
+    ap.add_argument("--frames", type=int, default=1000, help="frames per GPU per step (device-resident leg)")
+    ap.add_argument("--frames-per-launch", type=int, default=4)
+    ap.add_argument("--e2e-frames", type=int, default=128, help="frames per step of the host-buffer leg")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-sample", type=int, default=3, help="frames timed for the cpu_baseline object")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------
+# synthetic workload: rotated periodic board, Gaussian-bump displacement
+# --------------------------------------------------------------------------------------
+def make_frames_gpu(n, count, seed, device, chunk=8):
+    import torch
+
+    from oracle import fcd_oracle as o  # generator parameters only (host scalars)
+    rng = np.random.default_rng(seed)
+    a, b, eps = 60.0 * n / 1024.0, 3.0 * n / 1024.0, 0.1
+    ref = torch.from_numpy(o.rotated_board(n)).to(device)
+    frames = torch.empty((count, n, n), dtype=torch.float32, device=device)
+    y = torch.arange(n, dtype=torch.float64, device=device)[None, :, None]
+    x = torch.arange(n, dtype=torch.float64, device=device)[None, None, :]
+    two_pi = 2.0 * np.pi
+    for c0 in range(0, count, chunk):
+        c1 = min(count, c0 + chunk)
+        m = c1 - c0
+        cy = torch.tensor(rng.uniform(0.35 * n, 0.65 * n, m), device=device)[:, None, None]
+        cx = torch.tensor(rng.uniform(0.35 * n, 0.65 * n, m), device=device)[:, None, None]
+        sg = torch.tensor(rng.uniform(n / 12.0, n / 6.0, m), device=device)[:, None, None]
+        pk = torch.tensor(rng.uniform(0.2, 0.8, m), device=device)[:, None, None]
+        dy, dx = y - cy, x - cx
+        g = torch.exp(-(dy * dy + dx * dx) / (2.0 * sg * sg))
+        amp = pk * sg * np.exp(0.5)
+        uy = amp * dy / (sg * sg) * g          # u = -H grad h, H = 1
+        ux = amp * dx / (sg * sg) * g
+        yy, xx = y - uy, x - ux
+        A = two_pi * (a * yy + b * xx) / n
+        B = two_pi * (-b * yy + a * xx) / n
+        img = 0.5 + 0.25 * ((1.0 + eps) * torch.cos(A - B) - torch.cos(A + B)) / (1.0 + eps / 2.0)
+        frames[c0:c1] = img.to(torch.float32)
+        del g, uy, ux, yy, xx, A, B, img
+    return ref, frames
+
+
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [t.strip() for t in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------
+def cpu_frames(n, count, seed):
+    from oracle import fcd_oracle as o
+    ref, frames, _ = o.synthetic_frames(n, count, seed=seed)
+    return ref, frames
+
+
+def _cpu_one(args):
+    """One reference call as the reference makes it (carriers recomputed per frame, fcd.py:27)."""
+    ref, frame, sq = args
+    from oracle import fcd_oracle as o
+    hm, _, _ = o.compute_height_map(ref, frame, sq, height=1.0)
+    return float(hm[0, 0])
+
+
+def cpu_baseline_single(n, sample):
+    """cpu_baseline object: the oracle port, one process, scipy's default single FFT thread."""
+    from oracle import fcd_oracle as o
+    ref, frames = cpu_frames(n, sample, SEED)
+    sq = o.board_square_size(n)
+    _cpu_one((ref, frames[0], sq))  # warm (imports, compiles the unwrap helper)
+    t0 = time.perf_counter()
+    for i in range(sample):
+        _cpu_one((ref, frames[i], sq))
+    dt = time.perf_counter() - t0
+    return {"value": sample / dt, "unit": "frames/s", "cores": 1, "kind": "port",
+            "sample": f"{sample} frames {n}x{n} float32->float64, fcd.compute_height_map as the reference calls it "
+                      f"(carriers recomputed per frame, Herraez unwrap), oracle/fcd_oracle.py"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the Python reference cannot
+    travel to the GPU box) on all host cores, one process per core, frames split evenly."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+
+    from oracle import fcd_oracle as o
+    n = args.size
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 32))
+    ref, frames = cpu_frames(n, procs, SEED)
+    sq = o.board_square_size(n)
+    o.unwrap_phase(np.zeros((4, 4)))  # build the C helper before forking
+    work = [(ref, frames[i], sq) for i in range(procs)]
+    with mp.get_context("fork").Pool(procs) as pool:
+        for _ in range(args.warmup):
+            pool.map(_cpu_one, work)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_cpu_one, work)
+        dt = time.perf_counter() - t0
+    fps = procs * args.steps / dt
+    sample = (f"{procs} frames {n}x{n} per step (one per worker process), fcd.compute_height_map as the reference "
+              f"calls it, float64, oracle port of /root/reference/pyfcd")
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{n}x{n} synthetic checkerboard frames, one reference (BASELINE configs[1] shape)",
+                       "frames_per_step": procs, "size": n},
+            "mpix_per_s": fps * n * n / 1e6,
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": procs, "kind": "port", "sample": sample,
+                             "host_cpu_count": cores},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from fcd_b200 import HeightMapPlan
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n, F = args.size, args.frames
+    P = n * n
+    plan = HeightMapPlan((n, n), args.frames_per_launch, dev)
+    ref, frames = make_frames_gpu(n, F, SEED + rank, dev)
+    from oracle import fcd_oracle as o
+    sq = o.board_square_size(n)
+    cal = plan.bind(ref, square_size=sq, height=1.0)
+    out = torch.empty_like(frames)
+    torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        plan.execute(frames, out=out)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    plan.set_profiling(True)
+    launches0 = plan.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        plan.execute(frames, out=out)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = plan.launch_count - launches0
+    stages = plan.stage_times()
+    plan.set_profiling(False)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * F * args.steps / (ms_max * 1e-3)
+
+    # sanity: the timed output is a real height map (finite, zero mean, non-trivial)
+    chk = out[:: max(1, F // 8)]
+    assert bool(torch.isfinite(chk).all()) and float(chk.abs().max()) > 0
+
+    # ---- e2e: host pinned buffers through the public API, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        E = min(args.e2e_frames, F)
+        c = min(32, E)
+        h_in = torch.empty((E, n, n), dtype=torch.float32).pin_memory()
+        h_in.copy_(frames[:E].cpu())
+        h_out = torch.empty((E, n, n), dtype=torch.float32).pin_memory()
+        d_in = [torch.empty((c, n, n), dtype=torch.float32, device=dev) for _ in range(2)]
+        d_out = [torch.empty((c, n, n), dtype=torch.float32, device=dev) for _ in range(2)]
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+
+        def e2e_step():
+            ev_in = [None, None]
+            ev_done = [None, None]
+            ev_out = [None, None]
+            k = 0
+            for c0 in range(0, E, c):
+                c1 = min(E, c0 + c)
+                b = k & 1
+                with torch.cuda.stream(s_in):
+                    if ev_done[b] is not None:
+                        s_in.wait_event(ev_done[b])       # compute that last read this buffer
+                    d_in[b][: c1 - c0].copy_(h_in[c0:c1], non_blocking=True)
+                    ev_in[b] = torch.cuda.Event()
+                    ev_in[b].record(s_in)
+                main.wait_event(ev_in[b])
+                if ev_out[b] is not None:
+                    main.wait_event(ev_out[b])            # D2H that last read this output buffer
+                plan.execute(d_in[b][: c1 - c0], out=d_out[b][: c1 - c0])
+                ev_done[b] = torch.cuda.Event()
+                ev_done[b].record(main)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_done[b])
+                    h_out[c0:c1].copy_(d_out[b][: c1 - c0], non_blocking=True)
+                    ev_out[b] = torch.cuda.Event()
+                    ev_out[b].record(s_out)
+                k += 1
+            torch.cuda.synchronize()
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        assert torch.equal(h_out[:4], out[:4].cpu()), "host-buffer leg disagrees with the device-resident leg"
+        e2e = {"value": world * E * args.e2e_steps / float(tt.item()), "unit": "frames/s",
+               "h2d_bytes_per_step": int(E * P * 4), "d2h_bytes_per_step": int(E * P * 4),
+               "frames_per_step": E, "steps": args.e2e_steps,
+               "api": "fcd_b200.HeightMapPlan.execute on pinned host buffers, 32-frame chunks, copy/compute overlap"}
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        dom = max((k for k in stages if stages[k][1] > 0), key=lambda k: stages[k][0])
+        dom_ms, dom_launches, dom_frames = stages[dom]
+        alg_bytes_per_launch = 8.0 * P * (dom_frames / dom_launches)
+        achieved = alg_bytes_per_launch / (dom_ms / dom_launches * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(dom)
+        except Exception:
+            pass
+        total_stage_ms = sum(v[0] for v in stages.values())
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_frame": 8 * P,
+                    "kernel_share_of_step": dom_ms / total_stage_ms,
+                    "pipeline_achieved_gbs": value / world * 8 * P / 1e9,
+                    "pipeline_frac": value / world * 8 * P / 1e9 / peak,
+                    "stage_us_per_frame": {k: (v[0] * 1e3 / v[2] if v[2] else 0.0) for k, v in stages.items()}}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline_single(n, args.cpu_sample)
+        line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"batch of {F} frames {n}x{n} float32 per GPU, one reference "
+                                       f"(BASELINE.json configs[1])", "frames_per_gpu": F, "size": n,
+                           "frames_per_launch": args.frames_per_launch, "unwrap": True,
+                           "l2": f"inputs {F * P * 4 / 1e9:.1f} GB per step are larger than the 126 MB L2 (no flush needed)",
+                           "calibration_factor": cal, "parallelism": f"frame-sharded x{world}, no hot-path collective"},
+                "mpix_per_s": value * P / 1e6, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,103 @@
+/*
+ * fcd_b200.h -- C ABI of the B200-native fast-checkerboard-demodulation (FCD) path.
+ *
+ * The reference (Trapped-modes-2025-LTG/Trapped-Modes-LTG, /root/reference) is pure Python
+ * and has no FFI of its own; its boundary for this path is the classmethod surface of
+ * pyfcd.  Each entry point below names the reference interface it
+ * replaces.  All pointers named *_dev are CUDA device pointers on the device that was
+ * current when the plan was created; `stream` is a cudaStream_t (NULL = default stream).
+ * No torch types, no exceptions: every function returns 0 on success or a negative code,
+ * and fcd_last_error() returns the message of the last failure on the calling thread.
+ * A plan is bound to one device and may be used from one stream at a time.
+ * Supported shapes: rows and cols powers of two in [64, 4096].
+ */
+#ifndef FCD_B200_H
+#define FCD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fcd_plan fcd_plan;
+
+#define FCD_OK 0
+#define FCD_ERR_INVALID (-1)   /* bad argument / unsupported shape */
+#define FCD_ERR_RUNTIME (-2)   /* CUDA failure */
+#define FCD_ERR_STATE (-3)     /* call order (e.g. execute before bind) */
+#define FCD_ERR_NOPEAKS (-4)   /* no carrier candidate (reference: ValueError from min([]), fourier.py:38) */
+
+/* Create a plan for rows x cols frames.  `frames_per_launch` frames are processed per kernel
+ * wave (workspace is sized for that many); any batch size may be passed to fcd_execute.
+ * Replaces: nothing in the reference (it is stateless and recomputes everything per call,
+ * pyfcd/fcd.py:27); this is the hoisting of the per-reference work. */
+int fcd_plan_create(int rows, int cols, int frames_per_launch, fcd_plan** out);
+int fcd_plan_destroy(fcd_plan* plan);
+const char* fcd_last_error(void);
+
+/* fftshift(|fft2(image - mean)|) with k^2 <= (4 pi / min(shape))^2 zeroed, and its maximum.
+ * Replaces pyfcd/fourier.py:18-23,34 (front half of fourier.find_peaks) and
+ * pyfcd/fcd.py:149-155 (fcd.fft_peaks).  spectrum_dev: rows*cols float64 or NULL. */
+int fcd_highpass_spectrum(fcd_plan* plan, const void* image_dev, int image_is_f64,
+                          double* spectrum_dev, double* max_out, void* stream);
+
+/* Threshold, clear the four border lines, 8-connected blobs, per-blob first maximum,
+ * stable ascending sort by that maximum, first max_peaks.  Replaces
+ * pyfcd/fourier.py:140-168 (fourier.find_peak_locations).  rc_out: 2*max_peaks ints
+ * (row, col) on the host. */
+int fcd_peak_locations(fcd_plan* plan, const double* image_dev, double threshold, int max_peaks,
+                       int* rc_out, int* count_out, void* stream);
+
+/* (rightmost, perpendicular) carrier pixels in shifted coordinates:
+ * peaks_out = {r0, c0, r1, c1}.  Replaces pyfcd/fourier.py:8-41 (fourier.find_peaks). */
+int fcd_find_peaks(fcd_plan* plan, const void* image_dev, int image_is_f64, int peaks_out[4], void* stream);
+
+/* Per-reference state: disk masks, ccsgn = conj(ifft2(fft2(ref) * mask)) for both carriers,
+ * carrier wavevectors and the folded integration coefficients.  Replaces
+ * pyfcd/carriers.py:10-24 (Carrier.__init__) for both carriers plus the per-call constants
+ * of pyfcd/fcd.py:123-138 and pyfcd/fourier.py:128-132.  peaks = {r0,c0,r1,c1} shifted. */
+int fcd_bind_reference(fcd_plan* plan, const void* reference_dev, int reference_is_f64,
+                       const int peaks[4], double radius, double calibration_factor,
+                       double height, void* stream);
+
+/* The per-frame path: frames_dev[n][rows][cols] float32 -> height_dev[n][rows][cols] float32
+ * (+ optional phases_dev[n][2][rows][cols] float32).  Replaces pyfcd/fcd.py:28-33:
+ * fft2(displaced) -> compute_phases (fcd.py:104-120, incl. unwrap_phase when unwrap != 0)
+ * -> compute_displacement_field (fcd.py:123-138) -> -u/height -> integrate_in_fourier
+ * (fourier.py:116-137).  Optional mask_dev (uint8, nonzero = masked): the frame is replaced
+ * by the reference under the mask before the transform and the height map is zeroed under
+ * it afterwards (pydata/analyze.py:229-234,254-255); mask_stride = elements between
+ * consecutive frames' masks (0: one mask for all frames). */
+int fcd_execute(fcd_plan* plan, const float* frames_dev, int n_frames, float* height_dev,
+                float* phases_dev, const uint8_t* mask_dev, long long mask_stride, int unwrap,
+                void* stream);
+
+/* Carrier attributes (pyfcd/carriers.py:14-15): boolean mask in unshifted layout and ccsgn
+ * as complex128 (as_c128 != 0) or complex64. */
+int fcd_get_carrier_mask(fcd_plan* plan, int carrier, uint8_t* mask_dev, void* stream);
+int fcd_get_carrier_ccsgn(fcd_plan* plan, int carrier, void* ccsgn_dev, int as_c128, void* stream);
+
+/* Stage-level float64 building blocks used by the drop-in classmethods that take
+ * user-supplied intermediates (fcd.compute_phases with an arbitrary displaced_fft,
+ * fourier.integrate_in_fourier): in-place-capable 2-D complex128 FFT, direction -1 forward
+ * / +1 inverse (inverse scaled by 1/(rows*cols) like scipy.fft.ifft2). */
+int fcd_fft2_c128(fcd_plan* plan, const void* in_dev, void* out_dev, int direction, void* stream);
+
+/* Per-stage device timing for benchmarks: when enabled, fcd_execute brackets every stage
+ * with CUDA events on the launch stream.  Stages: 0 row-forward, 1 column band-pass,
+ * 2 row demodulation, 3 row linking, 4 phase fix-up, 5 column integration, 6 row inverse.
+ * fcd_stage_times synchronises the device and returns accumulated milliseconds, launches
+ * and frames per stage since profiling was last enabled. */
+int fcd_set_profiling(fcd_plan* plan, int enable);
+int fcd_stage_times(fcd_plan* plan, double ms_out[7], long long launches_out[7], long long frames_out[7]);
+
+/* Introspection for benchmarks: number of kernel launches issued through this plan and the
+ * padded number of band columns per carrier (workspace geometry). */
+long long fcd_launch_count(const fcd_plan* plan);
+int fcd_band_columns(const fcd_plan* plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FCD_B200_H */

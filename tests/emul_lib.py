@@ -1,0 +1,119 @@
+"""TEST INFRASTRUCTURE ONLY: builds and wraps tests/emul/libfcd_emul.so -- the product's
+kernel sources compiled with -DFCD_EMULATE so that every block / phase / thread runs
+sequentially on the CPU ("device" pointers are host pointers).  It lets the CPU test-suite
+check the exact kernel arithmetic and index maps in a container without a GPU.  The product
+package never imports this."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "trapped-modes-ltg_b200")
+CSRC = os.path.join(PKG, "csrc")
+EMUL_DIR = os.path.join(ROOT, "tests", "emul")
+LIB = os.path.join(EMUL_DIR, "libfcd_emul.so")
+if PKG not in sys.path:
+    sys.path.insert(0, PKG)
+
+from fcd_b200 import _native  # noqa: E402  (prototypes only; does not load the CUDA library)
+
+
+def build_emul() -> str:
+    srcs = [os.path.join(EMUL_DIR, "fcd_emul.cpp")] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    srcs.append(os.path.join(ROOT, "include", "fcd_b200.h"))
+    if (not os.path.exists(LIB)) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wno-unknown-pragmas", "-DFCD_EMULATE", "-shared", "-fPIC",
+                               "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB,
+                               os.path.join(EMUL_DIR, "fcd_emul.cpp")])
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = _native.declare(ctypes.CDLL(build_emul()))
+    return _lib
+
+
+def _p(a):
+    return ctypes.c_void_p(0 if a is None else a.ctypes.data)
+
+
+class EmulPlan:
+    """numpy-buffer twin of fcd_b200.engine.HeightMapPlan on the emulation library."""
+
+    def __init__(self, shape, frames_per_launch=2):
+        self.lib = lib()
+        self.shape = tuple(int(s) for s in shape)
+        self.h = ctypes.c_void_p()
+        _native.check(self.lib, self.lib.fcd_plan_create(self.shape[0], self.shape[1], frames_per_launch, ctypes.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.lib.fcd_plan_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def find_peaks(self, image):
+        img = np.ascontiguousarray(image)
+        assert img.dtype in (np.float32, np.float64)
+        out = (ctypes.c_int * 4)()
+        _native.check(self.lib, self.lib.fcd_find_peaks(self.h, _p(img), int(img.dtype == np.float64), out, None))
+        return np.array([out[0], out[1]]), np.array([out[2], out[3]])
+
+    def highpass_spectrum(self, image):
+        img = np.ascontiguousarray(image)
+        spec = np.empty(self.shape, np.float64)
+        mx = ctypes.c_double()
+        _native.check(self.lib, self.lib.fcd_highpass_spectrum(self.h, _p(img), int(img.dtype == np.float64), _p(spec),
+                                                               ctypes.byref(mx), None))
+        return spec, mx.value
+
+    def peak_locations(self, image, threshold, no_peaks):
+        img = np.ascontiguousarray(image, dtype=np.float64)
+        rc = (ctypes.c_int * (2 * max(no_peaks, 1)))()
+        cnt = ctypes.c_int()
+        _native.check(self.lib, self.lib.fcd_peak_locations(self.h, _p(img), float(threshold), no_peaks, rc,
+                                                            ctypes.byref(cnt), None))
+        return [np.array([rc[2 * i], rc[2 * i + 1]]) for i in range(cnt.value)]
+
+    def bind(self, reference, peaks, radius, cal, height=1.0):
+        ref = np.ascontiguousarray(reference)
+        pk = (ctypes.c_int * 4)(int(peaks[0][0]), int(peaks[0][1]), int(peaks[1][0]), int(peaks[1][1]))
+        _native.check(self.lib, self.lib.fcd_bind_reference(self.h, _p(ref), int(ref.dtype == np.float64), pk,
+                                                            float(radius), float(cal), float(height), None))
+
+    def execute(self, frames, phases=False, mask=None, unwrap=True):
+        fr = np.ascontiguousarray(frames, dtype=np.float32)
+        if fr.ndim == 2:
+            fr = fr[None]
+        out = np.zeros_like(fr)
+        ph = np.zeros((fr.shape[0], 2) + self.shape, np.float32) if phases else None
+        mk, stride = None, 0
+        if mask is not None:
+            mk = np.ascontiguousarray(mask, dtype=np.uint8)
+            stride = self.shape[0] * self.shape[1] if mk.ndim == 3 else 0
+        _native.check(self.lib, self.lib.fcd_execute(self.h, _p(fr), fr.shape[0], _p(out), _p(ph), _p(mk), stride,
+                                                     int(unwrap), None))
+        return (out, ph) if phases else out
+
+    def mask(self, i):
+        m = np.zeros(self.shape, np.uint8)
+        _native.check(self.lib, self.lib.fcd_get_carrier_mask(self.h, i, _p(m), None))
+        return m.astype(bool)
+
+    def ccsgn(self, i, c128=True):
+        c = np.zeros(self.shape, np.complex128 if c128 else np.complex64)
+        _native.check(self.lib, self.lib.fcd_get_carrier_ccsgn(self.h, i, _p(c), int(c128), None))
+        return c
+
+    def fft2(self, x, inverse=False):
+        a = np.ascontiguousarray(x, dtype=np.complex128)
+        out = np.empty_like(a)
+        _native.check(self.lib, self.lib.fcd_fft2_c128(self.h, _p(a), _p(out), 1 if inverse else -1, None))
+        return out

@@ -1,0 +1,174 @@
+"""CPU: the product's kernel sources, compiled for CPU emulation (tests/emul_lib.py), against
+the oracle and the reference-derived golden vectors.  This is what guards the kernel
+arithmetic and index maps in the GPU-less build container; the same comparisons run on the
+real device in tests/test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+from oracle import fcd_oracle as o
+from tests.emul_lib import EmulPlan, lib
+from fcd_b200 import _native
+
+
+def rel_l2(a, b):
+    return np.linalg.norm(np.ravel(a).astype(np.float64) - np.ravel(b)) / np.linalg.norm(np.ravel(b))
+
+
+def bind_like_reference(plan, ref, square_size, height=1.0):
+    peaks = plan.find_peaks(ref)
+    k = o.pixel_to_wavenumber(ref.shape, [peaks[0], peaks[1]])
+    cal = 2 * square_size / (2 * np.pi / np.mean(np.abs(k)))
+    radius = np.linalg.norm(peaks[0] - peaks[1]) / 2
+    plan.bind(ref, peaks, radius, cal, height)
+    return peaks, radius, cal
+
+
+def phase_offset_dev(ph, ref):
+    k = np.rint(np.median((ph - ref) / (2 * np.pi)))
+    return np.abs(ph - ref - 2 * np.pi * k).max()
+
+
+@pytest.mark.parametrize("case", ["small", "wrap"])
+def test_golden_synthetic(golden, case):
+    g = lambda k: golden[f"synth256_{case}.{k}"]
+    plan = EmulPlan((256, 256))
+    peaks, radius, cal = bind_like_reference(plan, g("ref").astype(np.float64), float(g("square_size")))
+    assert np.array_equal(np.array(peaks), g("pixels"))          # identical carrier pixels
+    assert cal == float(g("cal")) and radius == float(g("radius"))
+    hm, ph = plan.execute(np.stack([g("frame")] * 3), phases=True)   # 3 frames: two launch chunks
+    for i in range(3):
+        assert rel_l2(hm[i], g("height_map")) < 1e-5                 # budget 1e-4 (north star)
+    assert np.array_equal(hm[0], hm[1]) and np.array_equal(hm[0], hm[2])
+    _, pho, _ = o.compute_height_map(g("ref"), g("frame"), float(g("square_size")), height=1.0)
+    for i in range(2):
+        assert phase_offset_dev(ph[0, i], pho[i]) < 2e-5
+    plan.close()
+
+
+def test_validator_case_with_given_carriers(golden):
+    """val.py's axis-aligned board: its 'rightmost' choice is a 1-ulp tie, so the
+    reference's carriers are passed in; the surface wraps, exercising the unwrap kernels."""
+    I0, I = golden["val256.I0"], golden["val256.I"]
+    pix = golden["val256.pixels"]
+    plan = EmulPlan((256, 256), 1)
+    plan.bind(I0, pix, float(golden["val256.radius"]), float(golden["val256.cal"]), 1.0)
+    hm = plan.execute(I.astype(np.float32))
+    # float32 frame vs the reference's float64 frame: compare with the oracle on the same input
+    hmo, _, _ = o.compute_height_map(I0, I.astype(np.float32), 256 / 30, height=1)
+    assert rel_l2(hm[0], hmo) < 1e-5
+    assert rel_l2(hm[0], golden["val256.height_map"]) < 1e-4
+    hm_nw = plan.execute(I.astype(np.float32), unwrap=False)
+    assert rel_l2(hm_nw[0], hmo) > 0.1
+    plan.close()
+
+
+@pytest.mark.parametrize("i", [0, 1, 2])
+def test_carrier_search_camera_like(golden, i):
+    img = golden[f"noisy{i}.image"]
+    plan = EmulPlan(img.shape)
+    for dtype in (np.float64, np.float32):
+        peaks = plan.find_peaks(img.astype(dtype))
+        assert np.array_equal(np.array(peaks), golden[f"noisy{i}.peaks"])
+    spec, mx = plan.highpass_spectrum(img.astype(np.float64))
+    ospec = o.highpassed_spectrum(img.astype(np.float64))
+    assert np.allclose(spec, ospec, rtol=0, atol=1e-9 * ospec.max())
+    assert np.array_equal(spec == 0, ospec == 0)                   # same high-pass support
+    locs = plan.peak_locations(ospec, 0.5 * ospec.max(), 4)
+    assert [l.tolist() for l in locs] == [l.tolist() for l in o.find_peak_locations(ospec, 0.5 * ospec.max(), 4)]
+    plan.close()
+
+
+def test_peak_locations_semantics():
+    """ascending sort, first four, border lines cleared, 8-connectivity, first maximum."""
+    img = np.zeros((64, 64))
+    img[10, 10], img[11, 11], img[10, 12] = 5.0, 7.0, 7.0      # one blob (diagonals), max 7 first at (10,12)
+    img[30, 5] = 9.0
+    img[40, 40] = 3.0
+    img[50, 20] = 4.0
+    img[20, 50] = 8.0
+    img[0, 30] = img[63, 7] = img[17, 0] = img[33, 63] = 100.0   # on the border: ignored
+    plan = EmulPlan((64, 64))
+    got = [l.tolist() for l in plan.peak_locations(img, 1.0, 4)]
+    want = [l.tolist() for l in o.find_peak_locations(img, 1.0, 4)]
+    assert got == want == [[40, 40], [50, 20], [10, 12], [20, 50]]
+    assert plan.peak_locations(img, 1000.0, 4) == []
+    with pytest.raises(ValueError):
+        plan.find_peaks(np.zeros((64, 64)))                      # reference: min() of empty list
+    plan.close()
+
+
+@pytest.mark.parametrize("shape", [(64, 64), (64, 128), (128, 64), (512, 256)])
+def test_rectangular_and_small_shapes(shape):
+    n0, n1 = shape
+    a0, b0 = n0 * 15.0 / 256, 1.0
+    y = np.arange(n0)[:, None].astype(np.float64)
+    x = np.arange(n1)[None, :].astype(np.float64)
+    ky, kx = 2 * np.pi * round(a0) / n0, 2 * np.pi * round(n1 * 15.0 / 256) / n1
+    cy, cx, s = 0.45 * n0, 0.55 * n1, min(n0, n1) / 7.0
+    hgt = 0.5 * s * np.exp(-((y - cy) ** 2 + (x - cx) ** 2) / (2 * s * s))
+    uy, ux = (y - cy) / s ** 2 * hgt, (x - cx) / s ** 2 * hgt
+
+    def board(yy, xx):
+        return (0.5 + 0.25 * (1.1 * np.cos(ky * yy + 0.3 * kx * xx * 0) * 0 + 1.1 * np.cos(ky * yy + b0 * 2 * np.pi * xx / n1)
+                              + np.cos(kx * xx - b0 * 2 * np.pi * yy / n0)) / 2.1).astype(np.float32)
+
+    ref, frame = board(y, x), board(y - uy, x - ux)
+    sq = 3.3
+    plan = EmulPlan(shape, 1)
+    peaks, radius, cal = bind_like_reference(plan, ref.astype(np.float64), sq, height=0.7)
+    assert [p.tolist() for p in peaks] == [p.tolist() for p in o.find_peaks(ref.astype(np.float64))]
+    hm, ph = plan.execute(frame, phases=True)
+    hmo, pho, calo = o.compute_height_map(ref, frame, sq, height=0.7)
+    assert cal == calo
+    assert rel_l2(hm[0], hmo) < 2e-5
+    plan.close()
+
+
+def test_carrier_attributes_and_fft2(golden):
+    ref = golden["synth256_small.ref"].astype(np.float64)
+    sq = float(golden["synth256_small.square_size"])
+    plan = EmulPlan((256, 256))
+    bind_like_reference(plan, ref, sq)
+    cars, _ = o.compute_carriers(ref, sq)
+    for i in range(2):
+        assert np.array_equal(plan.mask(i), cars[i].mask)
+        assert np.abs(plan.ccsgn(i) - cars[i].ccsgn).max() < 1e-13
+        assert np.abs(plan.ccsgn(i, c128=False) - cars[i].ccsgn).max() < 1e-6
+    rng = np.random.default_rng(0)
+    z = rng.standard_normal((256, 256)) + 1j * rng.standard_normal((256, 256))
+    assert np.abs(plan.fft2(z) - np.fft.fft2(z)).max() < 1e-10
+    assert np.abs(plan.fft2(z, inverse=True) - np.fft.ifft2(z)).max() < 1e-14
+    plan.close()
+
+
+def test_mask_workflow(golden):
+    """analyze.py:229-234,254-255: frame := where(mask, reference, frame); height *= ~mask."""
+    g = lambda k: golden[f"synth256_small.{k}"]
+    ref, frame, sq = g("ref"), g("frame"), float(g("square_size"))
+    mask = np.zeros((256, 256), bool)
+    mask[100:140, 90:150] = True
+    plan = EmulPlan((256, 256))
+    bind_like_reference(plan, ref, sq)
+    hm = plan.execute(frame, mask=mask)
+    sub = np.where(mask, ref, frame)
+    hmo, _, _ = o.compute_height_map(ref, sub, sq, height=1.0)
+    hmo *= ~mask
+    assert rel_l2(hm[0], hmo) < 1e-5
+    assert np.all(hm[0][mask] == 0)
+    hm2 = plan.execute(np.stack([frame, frame]), mask=np.stack([mask, np.zeros_like(mask)]))
+    assert np.array_equal(hm2[0], hm[0]) and rel_l2(hm2[1], g("height_map")) < 1e-5
+    plan.close()
+
+
+def test_error_behaviour():
+    l = lib()
+    import ctypes
+    h = ctypes.c_void_p()
+    assert l.fcd_plan_create(100, 256, 1, ctypes.byref(h)) == _native.FCD_ERR_INVALID      # not a power of two
+    assert b"powers of two" in l.fcd_last_error()
+    assert l.fcd_plan_create(256, 8192, 1, ctypes.byref(h)) == _native.FCD_ERR_INVALID
+    plan = EmulPlan((64, 64))
+    f = np.zeros((1, 64, 64), np.float32)
+    rc = l.fcd_execute(plan.h, f.ctypes.data, 1, f.ctypes.data, None, None, 0, 1, None)
+    assert rc == _native.FCD_ERR_STATE                                                       # execute before bind
+    plan.close()

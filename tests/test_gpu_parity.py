@@ -1,0 +1,220 @@
+"""GPU (B200): the CUDA path, called through the product's Python surface and the C ABI,
+against the float64 oracle and the reference-derived golden vectors.  Tolerance from the
+north star: relative L2 of the float32 height map <= 1e-4, identical carrier pixels."""
+import numpy as np
+import pytest
+
+from oracle import fcd_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    return np.linalg.norm(np.ravel(a) - np.ravel(b)) / np.linalg.norm(np.ravel(b))
+
+
+def phase_dev(ph, ref):
+    k = np.rint(np.median((ph - ref) / (2 * np.pi)))
+    return np.abs(ph - ref - 2 * np.pi * k).max()
+
+
+@pytest.fixture(scope="module")
+def api():
+    import torch
+    assert torch.cuda.is_available()
+    from pyfcd.fcd import fcd, fourier, Carrier
+    import fcd_b200
+    return dict(fcd=fcd, fourier=fourier, Carrier=Carrier, eng=fcd_b200, torch=torch)
+
+
+def test_native_library_is_loaded(api):
+    api["eng"].get_plan((64, 64))
+    assert any("libfcd_b200.so" in l for l in open("/proc/self/maps"))
+
+
+@pytest.mark.parametrize("case", ["small", "wrap"])
+def test_drop_in_compute_height_map_golden(api, golden, case):
+    g = lambda k: golden[f"synth256_{case}.{k}"]
+    hm, ph, cal = api["fcd"].compute_height_map(g("ref"), g("frame"), float(g("square_size")), height=1.0)
+    assert hm.dtype == np.float64 and hm.flags.writeable and ph.shape == (2, 256, 256)
+    assert cal == float(g("cal"))
+    assert rel_l2(hm, g("height_map")) < TOL
+    assert rel_l2(hm, g("height_map")) < 1e-5        # what float32 actually achieves
+    _, pho, _ = o.compute_height_map(g("ref"), g("frame"), float(g("square_size")), height=1.0)
+    for i in range(2):
+        assert phase_dev(ph[i], pho[i]) < 5e-5
+    hm *= ~np.zeros(hm.shape, bool)                   # callers do this in place (analyze.py:255)
+
+
+def test_carriers_identical_to_reference(api, golden):
+    g = lambda k: golden[f"synth256_small.{k}"]
+    carriers, cal = api["fcd"].compute_carriers(g("ref").astype(np.float64), float(g("square_size")))
+    assert np.array_equal(np.array([c.pixels for c in carriers]), g("pixels"))
+    assert np.allclose(np.array([c.frequencies for c in carriers]), g("freqs"), rtol=1e-15)
+    assert carriers[0].radius == float(g("radius")) and cal == float(g("cal"))
+    oc, _ = o.compute_carriers(g("ref").astype(np.float64), float(g("square_size")))
+    for a, b in zip(carriers, oc):
+        assert np.array_equal(a.mask, b.mask)
+        assert np.abs(a.ccsgn - b.ccsgn).max() < 1e-13
+    calf, peaks = api["fcd"].compute_calibration_factor(float(g("square_size")), g("ref"))
+    assert calf == cal
+
+
+@pytest.mark.parametrize("i", [0, 1, 2])
+def test_carrier_search_camera_like(api, golden, i):
+    img = golden[f"noisy{i}.image"]
+    for dtype in (np.float32, np.float64):
+        peaks = api["fourier"].find_peaks(img.astype(dtype))
+        assert np.array_equal(np.array(peaks), golden[f"noisy{i}.peaks"])
+    cal, _ = api["fcd"].compute_calibration_factor(0.0022, img.astype(np.float64))
+    assert cal == float(golden[f"noisy{i}.cal"])
+    spec = o.highpassed_spectrum(img.astype(np.float64))
+    got = api["fourier"].find_peak_locations(spec, 0.5 * spec.max(), 4)
+    assert [p.tolist() for p in got] == [p.tolist() for p in o.find_peak_locations(spec, 0.5 * spec.max(), 4)]
+
+
+def test_validator_surface_with_unwrap(api, golden):
+    """pyval/val.py surface (phases reach +-pi): carriers given (its tie is round-off decided)."""
+    I0, I = golden["val256.I0"], golden["val256.I"].astype(np.float32)
+    plan = api["eng"].HeightMapPlan((256, 256), 1)
+    pix = golden["val256.pixels"]
+    plan.bind(I0, calibration_factor=float(golden["val256.cal"]), height=1, peaks=(pix[0], pix[1]),
+              radius=float(golden["val256.radius"]))
+    hm = plan.execute(api["torch"].from_numpy(I).cuda()).cpu().numpy()
+    hmo, _, _ = o.compute_height_map(I0, I, 256 / 30, height=1)
+    assert rel_l2(hm, hmo) < 1e-5
+    assert rel_l2(hm, golden["val256.height_map"]) < TOL
+    hm_nw = plan.execute(api["torch"].from_numpy(I).cuda(), unwrap=False).cpu().numpy()
+    assert rel_l2(hm_nw, hmo) > 0.1
+    plan.close()
+
+
+def test_batched_api_matches_oracle_and_is_order_independent(api):
+    n = 256
+    rng = np.random.default_rng(5)
+    ref = o.rotated_board(n, a=15.0, b=1.0)
+    frames = []
+    for _ in range(7):
+        cy, cx = rng.uniform(0.35 * n, 0.65 * n, 2)
+        _, uy, ux = o.gaussian_bump_displacement(n, (cy, cx), rng.uniform(n / 12, n / 6), rng.uniform(0.2, 6.0))
+        frames.append(o.rotated_board(n, a=15.0, b=1.0, uy=uy, ux=ux))
+    frames = np.stack(frames)
+    sq = o.board_square_size(n, 15.0)
+    hm, ph, cal = api["eng"].compute_height_maps(ref, frames, sq, height=0.5, return_phases=True, frames_per_launch=3)
+    hm = hm.cpu().numpy()
+    carriers, calo = o.compute_carriers(ref.astype(np.float64), sq)
+    assert cal == calo
+    for i in range(7):
+        hmo, _ = o.height_map_from_carriers(frames[i], carriers, calo, 0.5)
+        assert rel_l2(hm[i], hmo) < 1e-5
+    # same frames, different batch positions / chunking -> bitwise identical (sharding invariant)
+    perm = np.array([3, 0, 6, 1, 5, 2, 4])
+    hm2, _, _ = api["eng"].compute_height_maps(ref, frames[perm], sq, height=0.5, frames_per_launch=2)
+    assert np.array_equal(hm2.cpu().numpy(), hm[perm])
+
+
+def test_config1_1024(api):
+    """BASELINE.json configs[0]: single 1024^2 synthetic checkerboard + Gaussian bump."""
+    n = 1024
+    ref, frames, truth = o.synthetic_frames(n, 1)
+    sq = o.board_square_size(n)
+    hm, ph, cal = api["fcd"].compute_height_map(ref, frames[0], sq, height=1.0)
+    hmo, pho, calo = o.compute_height_map(ref, frames[0], sq, height=1.0)
+    assert cal == calo == 1.0
+    assert rel_l2(hm, hmo) < 1e-5
+    carriers, _ = api["fcd"].compute_carriers(ref, sq)
+    assert [c.pixels.tolist() for c in carriers] == [[512 + 57, 512 + 63], [512 - 63, 512 + 57]]
+    t = truth[0] - truth[0].mean()
+    assert rel_l2(hm, t) < 0.05                       # FCD's own accuracy on this surface
+
+
+def test_full_size_2048_properties(api):
+    """BASELINE.json configs[1] shape.  One frame against the oracle, the rest through
+    size-independent properties: zero mean, reference -> flat, batch invariance, truth."""
+    torch = api["torch"]
+    n = 2048
+    ref, frames, truth = o.synthetic_frames(n, 3)
+    sq = o.board_square_size(n)
+    plan = api["eng"].HeightMapPlan((n, n), 2)
+    cal = plan.bind(ref, square_size=sq, height=1.0)
+    assert cal == 1.0
+    assert [p.tolist() for p in plan.peaks] == [[1138, 1150], [898, 1138]]
+    batch = torch.from_numpy(np.concatenate([frames, ref[None], frames[:1]])).cuda()
+    hm = plan.execute(batch).cpu().numpy()
+    hmo, _, _ = o.compute_height_map(ref, frames[0], sq, height=1.0)
+    assert rel_l2(hm[0], hmo) < 1e-5
+    assert np.array_equal(hm[0], hm[4])                                 # batch position invariance
+    assert np.abs(hm[3]).max() < 1e-4 * np.abs(hm[0]).max()             # reference frame -> flat
+    for i in range(3):
+        assert abs(hm[i].mean()) < 1e-5 * np.abs(hm[i]).max()          # DC bin is zero (fourier.py:130)
+        t = truth[i] - truth[i].mean()
+        assert rel_l2(hm[i], t) < 0.05
+    plan.close()
+
+
+def test_mask_workflow(api, golden):
+    g = lambda k: golden[f"synth256_small.{k}"]
+    torch = api["torch"]
+    ref, frame, sq = g("ref"), g("frame"), float(g("square_size"))
+    mask = np.zeros((256, 256), bool)
+    mask[100:140, 90:150] = True
+    hm, _, _ = api["eng"].compute_height_maps(ref, frame[None], sq, height=1.0, mask=torch.from_numpy(mask))
+    hm = hm.cpu().numpy()[0]
+    hmo, _, _ = o.compute_height_map(ref, np.where(mask, ref, frame), sq, height=1.0)
+    hmo *= ~mask
+    assert rel_l2(hm, hmo) < 1e-5 and np.all(hm[mask] == 0)
+
+
+@pytest.mark.parametrize("shape", [(64, 128), (512, 256), (4096, 64)])
+def test_rectangular(api, shape):
+    n0, n1 = shape
+    y = np.arange(n0)[:, None].astype(np.float64)
+    x = np.arange(n1)[None, :].astype(np.float64)
+    ky, kx = 2 * np.pi * round(n0 * 15.0 / 256) / n0, 2 * np.pi * round(n1 * 15.0 / 256) / n1
+    cy, cx, s = 0.45 * n0, 0.55 * n1, min(n0, n1) / 7.0
+    hgt = 0.5 * s * np.exp(-((y - cy) ** 2 + (x - cx) ** 2) / (2 * s * s))
+    uy, ux = (y - cy) / s ** 2 * hgt, (x - cx) / s ** 2 * hgt
+    board = lambda yy, xx: (0.5 + 0.25 * (1.1 * np.cos(ky * yy + 2 * np.pi * xx / n1)
+                                          + np.cos(kx * xx - 2 * np.pi * yy / n0)) / 2.1).astype(np.float32)
+    ref, frame = board(y, x), board(y - uy, x - ux)
+    hm, ph, cal = api["fcd"].compute_height_map(ref, frame, 3.3, height=0.7)
+    hmo, pho, calo = o.compute_height_map(ref, frame, 3.3, height=0.7)
+    assert cal == calo and rel_l2(hm, hmo) < 2e-5
+
+
+def test_stage_level_methods(api, golden):
+    g = lambda k: golden[f"synth256_wrap.{k}"]
+    ref, frame, sq = g("ref").astype(np.float64), g("frame").astype(np.float64), float(g("square_size"))
+    fcd, fourier = api["fcd"], api["fourier"]
+    carriers, cal = fcd.compute_carriers(ref, sq)
+    ph = fcd.compute_phases(np.fft.fft2(frame), carriers)
+    oc, _ = o.compute_carriers(ref, sq)
+    pho = o.compute_phases(np.fft.fft2(frame), oc)
+    for i in range(2):
+        assert phase_dev(ph[i], pho[i]) < 1e-9
+    uv = fcd.compute_displacement_field(pho, carriers)
+    assert np.allclose(uv, o.compute_displacement_field(pho, oc), rtol=1e-12, atol=1e-12)
+    key = "integrate64x128"
+    h = fourier.integrate_in_fourier(golden[key + ".gx"], golden[key + ".gy"], 0.37)
+    assert np.allclose(h, golden[key + ".h"], rtol=0, atol=1e-12)
+    kx, ky = fourier.wavenumber_meshgrid((64, 128))
+    okx, oky = o.wavenumber_meshgrid((64, 128))
+    assert np.array_equal(kx, okx) and np.array_equal(ky, oky)
+
+
+def test_errors_like_the_reference(api):
+    fcd = api["fcd"]
+    ref = o.rotated_board(256, a=15.0, b=1.0)
+    with pytest.raises(Warning):
+        fcd.compute_height_map(ref, ref, 1.0, layers=[[1, 1], [1, 1.3], [1, 1.3], [1, 1]], height=1.0)
+    with pytest.raises(ValueError):
+        fcd.compute_height_map(np.zeros((256, 256), np.float32), ref, 1.0)      # no carrier peak
+    with pytest.raises(Exception):
+        fcd.compute_height_map(np.zeros((100, 256), np.float32), np.zeros((100, 256), np.float32), 1.0)
+    layers = [[5.7e-2, 1.0003], [1.2e-2, 1.48899], [4.3e-2, 1.34], [80e-2, 1.0003]]
+    assert fcd.height_from_layers(layers) == o.height_from_layers(layers)
+    h1, _, _ = fcd.compute_height_map(ref, ref * 0.9 + 0.01, 1.0, layers)
+    assert h1.shape == (256, 256)

@@ -1,0 +1,101 @@
+"""CPU: host-side logic of the product and the C-ABI surface (no compute calls)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import scipy.fft as sfft
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shared_library_exports_every_declared_symbol():
+    from fcd_b200 import _native, build
+    lib_path = build.build()
+    header = open(os.path.join(ROOT, "include", "fcd_b200.h")).read()
+    declared = set(re.findall(r"\b(fcd_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_native.PROTOTYPES), declared ^ set(_native.PROTOTYPES)
+    lib = ctypes.CDLL(lib_path)
+    for name in declared:
+        assert hasattr(lib, name), name
+    # the product library is CUDA code for sm_100a
+    out = subprocess.run(["cuobjdump", "-lelf", lib_path], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_wavenumber_helpers_match_scipy():
+    from fcd_b200 import engine as e
+    for n in (64, 256, 1024):
+        for cal in (1, 0.37, 2.0e-4):
+            assert np.array_equal(e.wavenumber(n, cal), sfft.fftfreq(n, cal / (2 * np.pi)))
+            assert np.array_equal(e.wavenumber(n, cal, True), sfft.fftshift(sfft.fftfreq(n, cal / (2 * np.pi))))
+    from oracle import fcd_oracle as o
+    pk = [np.array([142, 144]), np.array([112, 142])]
+    assert np.array_equal(e.pixel_to_wavenumber((256, 256), pk), o.pixel_to_wavenumber((256, 256), pk))
+    assert np.array_equal(e.pixel_to_wavenumber((256, 512), pk[0], 0.5), o.pixel_to_wavenumber((256, 512), pk[0], 0.5))
+    assert e.calibration_from_peaks((256, 256), pk, 256 / 30) == 1.0
+
+
+def test_height_resolution_like_reference(golden):
+    from fcd_b200 import engine as e
+    layers = golden["layers.example"].tolist()
+    assert e.height_from_layers(layers) == float(golden["layers.height"])
+    assert e.resolve_height() == 1 and e.resolve_height(height=0.3) == 0.3
+    assert e.resolve_height(layers=layers) == float(golden["layers.height"])
+    with pytest.raises(Warning):
+        e.resolve_height(layers=layers, height=1.0)
+
+
+def test_shard_ranges_partition_the_frames():
+    from fcd_b200 import engine as e
+    for n in (0, 1, 7, 1000, 20000):
+        for w in (1, 2, 4, 8):
+            r = [e.shard_range(n, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[k][1] == r[k + 1][0] for k in range(w - 1))
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        e.shard_range(10, 2, 2)
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from pyfcd.fcd import fcd
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fcd.compute_height_map(np.zeros((64, 64), np.float32), np.zeros((64, 64), np.float32), 1.0)
+
+
+_WORKER = r'''
+import os, sys
+import torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "trapped-modes-ltg_b200"))
+from fcd_b200 import engine as e
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+n = 11
+full = torch.arange(n * 4 * 5, dtype=torch.float32).reshape(n, 4, 5)
+a, b = e.shard_range(n, dist.get_rank(), 2)
+out = e.gather_height_maps(full[a:b].clone(), n, dst=0, chunk_frames=2)
+if dist.get_rank() == 0:
+    assert torch.equal(out, full)
+    print("GATHER_OK")
+else:
+    assert out is None
+dist.barrier(); dist.destroy_process_group()
+'''
+
+
+def test_sharded_gather_two_ranks_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "GATHER_OK" in outs[0]

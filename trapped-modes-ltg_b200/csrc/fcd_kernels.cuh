@@ -1,0 +1,678 @@
+// fcd_kernels.cuh -- the fused FCD height-map pipeline as phase-structured kernels.
+//
+// Reference path being replaced (file:line in /root/reference):
+//   pyfcd/fcd.py:28        displaced_fft = fft2(displaced)                       -> K1 + K2
+//   pyfcd/fcd.py:118       -angle(ifft2(displaced_fft*mask) * ccsgn)             -> K2 + K3
+//   pyfcd/fcd.py:119       unwrap_phase                                          -> K3 + K3b (+ K4 col 0)
+//   pyfcd/fcd.py:123-138   2x2 carrier solve                                     -> K4 (folded coefficients)
+//   pyfcd/fcd.py:32        height_gradient = -displacement/height                -> K4 (folded)
+//   pyfcd/fourier.py:116-137 integrate_in_fourier (+ remove_degeneracy 76-92)    -> K3 (row fwd) + K4 + K5
+//
+// A "kernel" is a struct with compile-time THREADS / PHASES / SMEM_BYTES, a Params struct,
+// a per-thread State (registers that live across barriers) and
+//     template<int PH> static void phase(params, block x, block y, tid, smem, state)
+// Consecutive phases are separated by a block-wide barrier.  On the GPU the phases are
+// inlined into one __global__ function (fcd_launch.cuh); tests/emul runs the very same
+// phase bodies thread-by-thread on the CPU.
+//
+// Thread organisation: a block holds G groups of TPF = L/16 threads; each group owns one
+// transform at a time (see fft_core.cuh for the natural strided ownership t + TPF*m).
+#pragma once
+#include <cmath>
+#include "fft_core.cuh"
+
+namespace fcd {
+
+constexpr float kTwoPiF = 6.28318530717958647692f;
+constexpr float kInvTwoPiF = 0.15915494309189533577f;
+
+FCD_HD int imin(int a, int b) { return a < b ? a : b; }
+
+// common helpers -------------------------------------------------------------------------
+template <int L, int G>
+struct GroupLayout {
+    static constexpr int TPF = L / 16;
+    static constexpr int THREADS = G * TPF;
+    // per-group exchange buffer; the skew makes "lane = group" accesses conflict free
+    static constexpr int SKEW = (G > 1 && G <= 16) ? 16 / G : 0;
+    static constexpr int STRIDE = L + L / 16 + SKEW;  // elements
+};
+
+struct alignas(16) cf2 {
+    cf a, b;
+};
+
+// =========================================================================================
+// K1  row forward: two real rows packed into one complex FFT; emits only the columns that
+//     fall inside the two carrier disks, transposed:  w1[f][i][c'][y]  (y contiguous)
+// =========================================================================================
+struct RowFwdParams {
+    const float* frames;      // [F][H][W]
+    const float* reference;   // [H][W]   (mask substitution, may be null)
+    const uint8_t* mask;      // [F][H][W] or [H][W] (mask_stride = 0), may be null
+    long long mask_stride;    // elements between consecutive frames' masks
+    cf* w1;                   // [F][2][ncp][H]
+    const cf* tw;             // W_L table
+    int H, ncp;
+    int nc[2];                // columns per carrier
+    int kc0[2];               // signed column frequency of c' = 0
+};
+
+template <int L, int G>
+struct RowFwd {
+    using F = Fft<L, -1, float>;
+    using GL = GroupLayout<L, G>;
+    using Params = RowFwdParams;
+    static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 6;
+    static constexpr int SMEM_BYTES = G * GL::STRIDE * (int)sizeof(cf);
+    struct State { cf v[16]; };
+
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem, State& st) {
+        const int g = tid / TPF, t = tid % TPF;
+        cf* s = reinterpret_cast<cf*>(smem) + g * GL::STRIDE;
+        const int W = L;
+        if constexpr (PH == 0) {
+            const int ya = (bx * G + g) * 2;
+            const long long base = ((long long)by * p.H + ya) * W;
+            const float* fa = p.frames + base;
+            const float* fb = fa + W;
+            if (p.mask) {
+                const uint8_t* ma = p.mask + (long long)by * p.mask_stride + (long long)ya * W;
+                const uint8_t* mb = ma + W;
+                const float* ra = p.reference + (long long)ya * W;
+                const float* rb = ra + W;
+                FCD_UNROLL
+                for (int m = 0; m < 16; ++m) {
+                    const int x = t + TPF * m;
+                    st.v[m] = mk<float>(ma[x] ? ra[x] : fa[x], mb[x] ? rb[x] : fb[x]);
+                }
+            } else {
+                FCD_UNROLL
+                for (int m = 0; m < 16; ++m) {
+                    const int x = t + TPF * m;
+                    st.v[m] = mk<float>(fa[x], fb[x]);
+                }
+            }
+            F::stepA(st.v, t, s);
+        } else if constexpr (PH == 1) {
+            F::stepB(st.v, t, s, p.tw);
+        } else if constexpr (PH == 2) {
+            F::stepC(st.v, t, s);
+        } else if constexpr (PH == 3) {
+            F::stepD(st.v, t, s, p.tw);
+        } else if constexpr (PH == 4) {
+            FCD_UNROLL
+            for (int m = 0; m < 16; ++m) s[fft_pos(t + TPF * m)] = st.v[m];
+        } else {
+            const cf* sb = reinterpret_cast<const cf*>(smem);
+            const int total = 2 * p.ncp * G;
+            for (int item = tid; item < total; item += THREADS) {
+                const int gg = item % G, cc = item / G;
+                const int i = cc / p.ncp, c = cc % p.ncp;
+                if (c >= p.nc[i]) continue;
+                const int kc = p.kc0[i] + c;
+                const int k = kc < 0 ? -kc : kc;
+                const cf x1 = sb[gg * GL::STRIDE + fft_pos(k)];
+                const cf x2 = conj(sb[gg * GL::STRIDE + fft_pos((W - k) & (W - 1))]);
+                cf a = x1 + x2;              // 2 * rowA spectrum at k
+                cf b = mul_mi(x1 - x2);      // 2 * rowB spectrum at k
+                if (kc < 0) { a = conj(a); b = conj(b); }
+                const int ya = (bx * G + gg) * 2;
+                cf2 o; o.a = a; o.b = b;
+                *reinterpret_cast<cf2*>(p.w1 + (((long long)by * 2 + i) * p.ncp + c) * p.H + ya) = o;
+            }
+        }
+    }
+};
+
+// =========================================================================================
+// K2  column band-pass: forward FFT along y, keep the disk chord of this column, inverse
+//     FFT along y.   w1[f][i][c'][y]  ->  w2[f][i][y][c']  (c' contiguous)
+// =========================================================================================
+struct ColBandParams {
+    const cf* w1;
+    cf* w2;
+    const cf* tw;
+    const int* chord_lo;   // [2][ncp] first kept shifted row (inclusive)
+    const int* chord_hi;   // [2][ncp] last kept shifted row (inclusive); lo > hi: empty
+    int ncp;
+    int nc[2];
+    float scale;
+};
+
+template <int L, int G>
+struct ColBand {
+    using FF = Fft<L, -1, float>;
+    using FI = Fft<L, +1, float>;
+    using GL = GroupLayout<L, G>;
+    using Params = ColBandParams;
+    static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 10;
+    static constexpr int SMEM_BYTES = G * GL::STRIDE * (int)sizeof(cf);
+    struct State { cf v[16]; };
+
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem, State& st) {
+        const int g = tid / TPF, t = tid % TPF;
+        cf* s = reinterpret_cast<cf*>(smem) + g * GL::STRIDE;
+        const int H = L;
+        const int i = by & 1;
+        const int c = bx * G + g;
+        if constexpr (PH == 0) {
+            if (c < p.nc[i]) {
+                const cf* col = p.w1 + ((long long)by * p.ncp + c) * H;
+                FCD_UNROLL
+                for (int m = 0; m < 16; ++m) st.v[m] = col[t + TPF * m];
+            } else {
+                FCD_UNROLL
+                for (int m = 0; m < 16; ++m) st.v[m] = mk<float>(0.f, 0.f);
+            }
+            FF::stepA(st.v, t, s);
+        } else if constexpr (PH == 1) {
+            FF::stepB(st.v, t, s, p.tw);
+        } else if constexpr (PH == 2) {
+            FF::stepC(st.v, t, s);
+        } else if constexpr (PH == 3) {
+            FF::stepD(st.v, t, s, p.tw);
+            int lo = 1, hi = 0;
+            if (c < p.nc[i]) { lo = p.chord_lo[i * p.ncp + c]; hi = p.chord_hi[i * p.ncp + c]; }
+            FCD_UNROLL
+            for (int m = 0; m < 16; ++m) {
+                const int r = (t + TPF * m + H / 2) & (H - 1);  // shifted row of frequency index
+                const bool keep = (r >= lo) && (r <= hi);
+                st.v[m] = keep ? scale(st.v[m], p.scale) : mk<float>(0.f, 0.f);
+            }
+        } else if constexpr (PH == 4) {
+            FI::stepA(st.v, t, s);
+        } else if constexpr (PH == 5) {
+            FI::stepB(st.v, t, s, p.tw);
+        } else if constexpr (PH == 6) {
+            FI::stepC(st.v, t, s);
+        } else if constexpr (PH == 7) {
+            FI::stepD(st.v, t, s, p.tw);
+        } else if constexpr (PH == 8) {
+            FCD_UNROLL
+            for (int m = 0; m < 16; ++m) s[fft_pos(t + TPF * m)] = st.v[m];
+        } else {
+            const cf* sb = reinterpret_cast<const cf*>(smem);
+            for (int item = tid; item < G * H; item += THREADS) {
+                const int gg = item % G, y = item / G;
+                const int cc = bx * G + gg;
+                if (cc < p.nc[i]) p.w2[((long long)by * H + y) * p.ncp + cc] = sb[gg * GL::STRIDE + fft_pos(y)];
+            }
+        }
+    }
+};
+
+// =========================================================================================
+// K3  row demodulation: for both carriers inverse row FFT of the band, multiply by ccsgn,
+//     -atan2 -> wrapped phases; unwrap along the row (integer prefix sum of 2pi jumps,
+//     anchored at x_ref); forward row FFT of z = phi0 + i*phi1.
+//     w2[f][i][y][c'] -> w3[f][y][kc] (+ colphase[f][i][y] = wrapped phase at x_ref,
+//     + optional phases[f][i][y][x])
+// =========================================================================================
+struct RowDemodParams {
+    const cf* w2;
+    const cf* ccsgn;     // [2][H][W]
+    cf* w3;              // [F][H][W]
+    float* colphase;     // [F][2][H]
+    float* phases;       // [F][2][H][W] or null
+    const cf* tw;
+    int H, ncp;
+    int nc[2];
+    int kc0[2];
+    int x_ref;
+    int unwrap;
+};
+
+struct int2s { int a, b; };
+
+template <int L, int G>
+struct RowDemod {
+    using FF = Fft<L, -1, float>;
+    using FI = Fft<L, +1, float>;
+    using GL = GroupLayout<L, G>;
+    using Params = RowDemodParams;
+    static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 18;
+    // per group: exchange buffer (aliased by the jump scan), chunk totals, chunk offsets, flag
+    static constexpr int AUX_INTS = 4 * TPF + 4;
+    static constexpr int GROUP_BYTES = GL::STRIDE * (int)sizeof(cf) + AUX_INTS * (int)sizeof(int);
+    static constexpr int SMEM_BYTES = G * GROUP_BYTES;
+    struct State {
+        cf v[16];
+        float ph0[16], ph1[16];
+    };
+
+    FCD_HD static void load_band(const Params& p, int f, int i, int y, int t, cf* v) {
+        const int W = L;
+        const cf* row = p.w2 + (((long long)f * 2 + i) * p.H + y) * p.ncp;
+        FCD_UNROLL
+        for (int m = 0; m < 16; ++m) {
+            const int pidx = t + TPF * m;
+            const int kc = pidx < W / 2 ? pidx : pidx - W;
+            const int c = kc - p.kc0[i];
+            v[m] = (c >= 0 && c < p.nc[i]) ? row[c] : mk<float>(0.f, 0.f);
+        }
+    }
+    FCD_HD static void demod(const Params& p, int i, int y, int t, const cf* v, float* ph) {
+        const int W = L;
+        const cf* cc = p.ccsgn + ((long long)i * p.H + y) * W;
+        FCD_UNROLL
+        for (int m = 0; m < 16; ++m) {
+            const cf q = v[m] * cc[t + TPF * m];
+            ph[m] = -atan2f(q.y, q.x);
+        }
+    }
+
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem, State& st) {
+        const int g = tid / TPF, t = tid % TPF;
+        unsigned char* gbase = smem + (size_t)g * GROUP_BYTES;
+        cf* s = reinterpret_cast<cf*>(gbase);
+        int2s* sj = reinterpret_cast<int2s*>(gbase);  // aliases s (L + L/16 int2 <= buffer)
+        int* aux = reinterpret_cast<int*>(gbase + GL::STRIDE * sizeof(cf));
+        int2s* part = reinterpret_cast<int2s*>(aux);            // [TPF]
+        int2s* off = reinterpret_cast<int2s*>(aux + 2 * TPF);   // [TPF]
+        int* flag = aux + 4 * TPF;
+        const int W = L;
+        const int y = bx * G + g;
+        const int f = by;
+        if constexpr (PH == 0) {
+            if (t == 0) *flag = 0;
+            load_band(p, f, 0, y, t, st.v);
+            FI::stepA(st.v, t, s);
+        } else if constexpr (PH == 1) {
+            FI::stepB(st.v, t, s, p.tw);
+        } else if constexpr (PH == 2) {
+            FI::stepC(st.v, t, s);
+        } else if constexpr (PH == 3) {
+            FI::stepD(st.v, t, s, p.tw);
+            demod(p, 0, y, t, st.v, st.ph0);
+        } else if constexpr (PH == 4) {
+            load_band(p, f, 1, y, t, st.v);
+            FI::stepA(st.v, t, s);
+        } else if constexpr (PH == 5) {
+            FI::stepB(st.v, t, s, p.tw);
+        } else if constexpr (PH == 6) {
+            FI::stepC(st.v, t, s);
+        } else if constexpr (PH == 7) {
+            FI::stepD(st.v, t, s, p.tw);
+            demod(p, 1, y, t, st.v, st.ph1);
+            // wrapped phase at the anchor column links the rows (K3b)
+            if (t == (p.x_ref % TPF)) {
+                const int m = p.x_ref / TPF;
+                float a0 = 0.f, a1 = 0.f;
+                FCD_UNROLL
+                for (int mm = 0; mm < 16; ++mm)
+                    if (mm == m) { a0 = st.ph0[mm]; a1 = st.ph1[mm]; }
+                p.colphase[((long long)f * 2 + 0) * p.H + y] = a0;
+                p.colphase[((long long)f * 2 + 1) * p.H + y] = a1;
+            }
+        } else if constexpr (PH == 8) {
+            if (p.unwrap) {
+                FCD_UNROLL
+                for (int m = 0; m < 16; ++m) s[fft_pos(t + TPF * m)] = mk<float>(st.ph0[m], st.ph1[m]);
+            }
+        } else if constexpr (PH == 9) {
+            // jumps to the left neighbour; kept in v (as ints) until the buffer may be reused
+            if (p.unwrap) {
+                bool any = false;
+                FCD_UNROLL
+                for (int m = 0; m < 16; ++m) {
+                    const int x = t + TPF * m;
+                    int j0 = 0, j1 = 0;
+                    if (x > 0) {
+                        const cf prev = s[fft_pos(x - 1)];
+                        j0 = (int)rintf((st.ph0[m] - prev.x) * kInvTwoPiF);
+                        j1 = (int)rintf((st.ph1[m] - prev.y) * kInvTwoPiF);
+                    }
+                    any = any || (j0 != 0) || (j1 != 0);
+                    st.v[m].x = (float)j0;
+                    st.v[m].y = (float)j1;
+                }
+                if (any) *flag = 1;
+            }
+        } else if constexpr (PH == 10) {
+            if (p.unwrap && *flag) {
+                FCD_UNROLL
+                for (int m = 0; m < 16; ++m) {
+                    int2s j; j.a = (int)st.v[m].x; j.b = (int)st.v[m].y;
+                    sj[fft_pos(t + TPF * m)] = j;
+                }
+            }
+        } else if constexpr (PH == 11) {
+            if (p.unwrap && *flag) {   // inclusive scan of this thread's contiguous chunk
+                int a = 0, b = 0;
+                FCD_UNROLL
+                for (int q = 0; q < 16; ++q) {
+                    int2s j = sj[fft_pos(16 * t + q)];
+                    a += j.a; b += j.b;
+                    j.a = a; j.b = b;
+                    sj[fft_pos(16 * t + q)] = j;
+                }
+                int2s tot; tot.a = a; tot.b = b;
+                part[t] = tot;
+            }
+        } else if constexpr (PH == 12) {
+            if (p.unwrap && *flag) {
+                int a = 0, b = 0;
+                for (int q = 0; q < t; ++q) { a += part[q].a; b += part[q].b; }
+                int2s o; o.a = a; o.b = b;
+                off[t] = o;
+            }
+        } else if constexpr (PH == 13) {
+            if (p.unwrap && *flag) {
+                const int2s cr = sj[fft_pos(p.x_ref)];
+                const int2s orf = off[p.x_ref >> 4];
+                const int ra = cr.a + orf.a, rb = cr.b + orf.b;
+                FCD_UNROLL
+                for (int m = 0; m < 16; ++m) {
+                    const int x = t + TPF * m;
+                    const int2s c = sj[fft_pos(x)];
+                    const int2s o = off[x >> 4];
+                    st.ph0[m] -= kTwoPiF * (float)(c.a + o.a - ra);
+                    st.ph1[m] -= kTwoPiF * (float)(c.b + o.b - rb);
+                }
+            }
+            if (p.phases) {
+                float* o0 = p.phases + (((long long)f * 2 + 0) * p.H + y) * W;
+                float* o1 = p.phases + (((long long)f * 2 + 1) * p.H + y) * W;
+                FCD_UNROLL
+                for (int m = 0; m < 16; ++m) {
+                    o0[t + TPF * m] = st.ph0[m];
+                    o1[t + TPF * m] = st.ph1[m];
+                }
+            }
+            FCD_UNROLL
+            for (int m = 0; m < 16; ++m) st.v[m] = mk<float>(st.ph0[m], st.ph1[m]);
+        } else if constexpr (PH == 14) {
+            FF::stepA(st.v, t, s);
+        } else if constexpr (PH == 15) {
+            FF::stepB(st.v, t, s, p.tw);
+        } else if constexpr (PH == 16) {
+            FF::stepC(st.v, t, s);
+        } else {
+            FF::stepD(st.v, t, s, p.tw);
+            cf* o = p.w3 + ((long long)f * p.H + y) * W;
+            FCD_UNROLL
+            for (int m = 0; m < 16; ++m) o[t + TPF * m] = st.v[m];
+        }
+    }
+};
+
+// =========================================================================================
+// K3b row linking: integer prefix sum along y of the 2pi jumps of the anchor column.
+//     rowoff[f][i][y] = -2pi * (M(y) - M(y_ref));  also (optionally) finishes `phases`.
+// =========================================================================================
+struct RowLinkParams {
+    const float* colphase;  // [F][2][H]
+    float* rowoff;          // [F][2][H]
+    int H, y_ref;
+    int unwrap;
+};
+
+struct RowLink {
+    using Params = RowLinkParams;
+    static constexpr int THREADS = 256, PHASES = 4;
+    static constexpr int MAXH = 4096;
+    static constexpr int SMEM_BYTES = (MAXH + 2 * THREADS + 4) * (int)sizeof(int);
+    struct State { int dummy; };
+
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem, State&) {
+        int* c = reinterpret_cast<int*>(smem);
+        int* part = c + MAXH;
+        int* off = part + THREADS;
+        int* mref = off + THREADS;
+        const int H = p.H;
+        const int chunk = (H + THREADS - 1) / THREADS;
+        const int y0 = tid * chunk;
+        const float* cp = p.colphase + ((long long)by * 2 + bx) * H;
+        float* out = p.rowoff + ((long long)by * 2 + bx) * H;
+        if constexpr (PH == 0) {
+            int acc = 0;
+            for (int q = 0; q < chunk; ++q) {
+                const int y = y0 + q;
+                if (y < H) {
+                    if (y > 0 && p.unwrap) acc += (int)rintf((cp[y] - cp[y - 1]) * kInvTwoPiF);
+                    c[y] = acc;
+                }
+            }
+            part[tid] = acc;
+        } else if constexpr (PH == 1) {
+            int a = 0;
+            for (int q = 0; q < tid; ++q) a += part[q];
+            off[tid] = a;
+        } else if constexpr (PH == 2) {
+            if (tid == 0) *mref = c[p.y_ref] + off[p.y_ref / chunk];
+        } else {
+            for (int q = 0; q < chunk; ++q) {
+                const int y = y0 + q;
+                if (y < H) out[y] = -kTwoPiF * (float)(c[y] + off[tid] - *mref);
+            }
+        }
+    }
+};
+
+// adds the row offsets to a materialised phases array (only when phases are requested)
+struct PhaseFixParams {
+    float* phases;         // [F][2][H][W]
+    const float* rowoff;   // [F][2][H]
+    int H, W;
+};
+struct PhaseFix {
+    using Params = PhaseFixParams;
+    static constexpr int THREADS = 256, PHASES = 1, SMEM_BYTES = 16;
+    struct State { int dummy; };
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
+        // bx: row, by: f*2+i
+        const float o = p.rowoff[(long long)by * p.H + bx];
+        if (o != 0.f) {
+            float* row = p.phases + ((long long)by * p.H + bx) * p.W;
+            for (int x = tid; x < p.W; x += THREADS) row[x] += o;
+        }
+    }
+};
+
+// =========================================================================================
+// K4  column integration: forward FFT along y of columns kc and W-kc of z_row, split into
+//     the spectra of phi0 and phi1, apply the folded 2x2-solve / (-1/height) / (-i k / k^2)
+//     coefficients (Hermitian part, = np.real(ifft2(.))), inverse FFT along y.
+//     w3[f][y][kc] -> w4[f][y][kc], kc in [0, W/2]
+// =========================================================================================
+struct ColIntegrateParams {
+    const cf* w3;
+    const float* rowoff;   // [F][2][H]
+    cf* w4;                // [F][H][w4p]
+    const cf* tw;
+    const float* kx;       // [W]  column wavenumbers (plain, used for k^2)
+    const float* kxq;      // [W]  with index W/2+1 zeroed (fourier.py:89)
+    const float* ky;       // [H]
+    const float* kyq;      // [H]  with index H/2+1 zeroed (fourier.py:92)
+    int W, w4p;
+    float f0r, f0c, f1r, f1c;   // carrier wavevectors [k_row, k_col] (fcd.py:134-137)
+    float scale;                // 1 / (2 * height * det * H * W)
+    int unwrap;
+};
+
+template <int L, int G>
+struct ColIntegrate {
+    using FF = Fft<L, -1, float>;
+    using FI = Fft<L, +1, float>;
+    using GL = GroupLayout<L, G>;
+    using Params = ColIntegrateParams;
+    static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 16;
+    static constexpr int SMEM_BYTES = G * GL::STRIDE * (int)sizeof(cf);
+    struct State { cf v[16]; cf va[16]; };
+
+    FCD_HD static void load_col(const Params& p, int f, int kc, int t, cf* v) {
+        const int H = L;
+        const cf* base = p.w3 + (long long)f * H * p.W + kc;
+        FCD_UNROLL
+        for (int m = 0; m < 16; ++m) v[m] = base[(long long)(t + TPF * m) * p.W];
+        if (kc == 0 && p.unwrap) {
+            const float* r0 = p.rowoff + ((long long)f * 2 + 0) * H;
+            const float* r1 = p.rowoff + ((long long)f * 2 + 1) * H;
+            const float w = (float)p.W;
+            FCD_UNROLL
+            for (int m = 0; m < 16; ++m) {
+                v[m].x += w * r0[t + TPF * m];
+                v[m].y += w * r1[t + TPF * m];
+            }
+        }
+    }
+
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem, State& st) {
+        const int g = tid / TPF, t = tid % TPF;
+        cf* s = reinterpret_cast<cf*>(smem) + g * GL::STRIDE;
+        const int H = L;
+        const int f = by;
+        const int kc = bx * G + g;
+        const bool valid = kc <= p.W / 2;
+        const int kcm = (p.W - kc) & (p.W - 1);
+        if constexpr (PH == 0) {
+            if (valid) load_col(p, f, kc, t, st.v);
+            else { FCD_UNROLL for (int m = 0; m < 16; ++m) st.v[m] = mk<float>(0.f, 0.f); }
+            FF::stepA(st.v, t, s);
+        } else if constexpr (PH == 1) {
+            FF::stepB(st.v, t, s, p.tw);
+        } else if constexpr (PH == 2) {
+            FF::stepC(st.v, t, s);
+        } else if constexpr (PH == 3) {
+            FF::stepD(st.v, t, s, p.tw);
+            FCD_UNROLL
+            for (int m = 0; m < 16; ++m) st.va[m] = st.v[m];
+        } else if constexpr (PH == 4) {
+            if (valid) load_col(p, f, kcm, t, st.v);
+            else { FCD_UNROLL for (int m = 0; m < 16; ++m) st.v[m] = mk<float>(0.f, 0.f); }
+            FF::stepA(st.v, t, s);
+        } else if constexpr (PH == 5) {
+            FF::stepB(st.v, t, s, p.tw);
+        } else if constexpr (PH == 6) {
+            FF::stepC(st.v, t, s);
+        } else if constexpr (PH == 7) {
+            FF::stepD(st.v, t, s, p.tw);
+        } else if constexpr (PH == 8) {
+            FCD_UNROLL
+            for (int m = 0; m < 16; ++m) s[fft_pos(t + TPF * m)] = st.v[m];
+        } else if constexpr (PH == 9) {
+            if (valid) {
+                const float kxv = p.kx[kc], kxa = p.kxq[kc], kxb = p.kxq[kcm];
+                FCD_UNROLL
+                for (int m = 0; m < 16; ++m) {
+                    const int kr = t + TPF * m;
+                    const int krm = (H - kr) & (H - 1);
+                    const cf zm = conj(s[fft_pos(krm)]);       // conj Z(-kr, -kc)
+                    const cf z = st.va[m];                      // Z(kr, kc)
+                    const cf p0 = z + zm;                       // 2 * Phi0(k)
+                    const cf p1 = mul_mi(z - zm);               // 2 * Phi1(k)
+                    const float kyv = p.ky[kr], kya = p.kyq[kr], kyb = p.kyq[krm];
+                    float k2 = kxv * kxv + kyv * kyv;
+                    if (kr == 0 && kc == 0) k2 = 1.f;
+                    const float ik2 = 1.0f / k2;
+                    // a(k), a(-k) and b(k), b(-k): coefficients of Phi0, Phi1 in hhat / i
+                    const float a_p = kxa * p.f1r - kya * p.f1c, a_m = kxb * p.f1r - kyb * p.f1c;
+                    const float b_p = kya * p.f0c - kxa * p.f0r, b_m = kyb * p.f0c - kxb * p.f0r;
+                    const float aH = 0.5f * (a_p - a_m) * ik2 * p.scale;
+                    const float bH = 0.5f * (b_p - b_m) * ik2 * p.scale;
+                    const cf acc = mk<float>(aH * p0.x + bH * p1.x, aH * p0.y + bH * p1.y);
+                    st.v[m] = mul_pi(acc);
+                }
+            } else {
+                FCD_UNROLL
+                for (int m = 0; m < 16; ++m) st.v[m] = mk<float>(0.f, 0.f);
+            }
+        } else if constexpr (PH == 10) {
+            FI::stepA(st.v, t, s);
+        } else if constexpr (PH == 11) {
+            FI::stepB(st.v, t, s, p.tw);
+        } else if constexpr (PH == 12) {
+            FI::stepC(st.v, t, s);
+        } else if constexpr (PH == 13) {
+            FI::stepD(st.v, t, s, p.tw);
+        } else if constexpr (PH == 14) {
+            FCD_UNROLL
+            for (int m = 0; m < 16; ++m) s[fft_pos(t + TPF * m)] = st.v[m];
+        } else {
+            const cf* sb = reinterpret_cast<const cf*>(smem);
+            for (int item = tid; item < G * H; item += THREADS) {
+                const int gg = item % G, y = item / G;
+                const int kk = bx * G + gg;
+                if (kk <= p.W / 2) p.w4[((long long)f * H + y) * p.w4p + kk] = sb[gg * GL::STRIDE + fft_pos(y)];
+            }
+        }
+    }
+};
+
+// =========================================================================================
+// K5  row inverse (c2r, two rows per transform):  w4[f][y][0..W/2] -> height[f][y][x]
+// =========================================================================================
+struct RowInvParams {
+    const cf* w4;
+    float* height;          // [F][H][W]
+    const uint8_t* mask;    // optional: height *= ~mask  (analyze.py:254-255)
+    long long mask_stride;
+    const cf* tw;
+    int H, w4p;
+};
+
+template <int L, int G>
+struct RowInv {
+    using FI = Fft<L, +1, float>;
+    using GL = GroupLayout<L, G>;
+    using Params = RowInvParams;
+    static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 4;
+    static constexpr int SMEM_BYTES = G * GL::STRIDE * (int)sizeof(cf);
+    struct State { cf v[16]; };
+
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem, State& st) {
+        const int g = tid / TPF, t = tid % TPF;
+        cf* s = reinterpret_cast<cf*>(smem) + g * GL::STRIDE;
+        const int W = L;
+        const int ya = (bx * G + g) * 2;
+        if constexpr (PH == 0) {
+            const cf* ra = p.w4 + ((long long)by * p.H + ya) * p.w4p;
+            const cf* rb = ra + p.w4p;
+            FCD_UNROLL
+            for (int m = 0; m < 16; ++m) {
+                const int pidx = t + TPF * m;
+                const bool lower = pidx <= W / 2;
+                const int k = lower ? pidx : W - pidx;
+                cf a = ra[k], b = rb[k];
+                if (k == 0 || k == W / 2) { a.y = 0.f; b.y = 0.f; }
+                if (!lower) { a = conj(a); b = conj(b); }
+                st.v[m] = a + mul_pi(b);
+            }
+            FI::stepA(st.v, t, s);
+        } else if constexpr (PH == 1) {
+            FI::stepB(st.v, t, s, p.tw);
+        } else if constexpr (PH == 2) {
+            FI::stepC(st.v, t, s);
+        } else {
+            FI::stepD(st.v, t, s, p.tw);
+            float* oa = p.height + ((long long)by * p.H + ya) * W;
+            float* ob = oa + W;
+            if (p.mask) {
+                const uint8_t* ma = p.mask + (long long)by * p.mask_stride + (long long)ya * W;
+                const uint8_t* mb = ma + W;
+                FCD_UNROLL
+                for (int m = 0; m < 16; ++m) {
+                    const int x = t + TPF * m;
+                    oa[x] = ma[x] ? 0.f : st.v[m].x;
+                    ob[x] = mb[x] ? 0.f : st.v[m].y;
+                }
+            } else {
+                FCD_UNROLL
+                for (int m = 0; m < 16; ++m) {
+                    oa[t + TPF * m] = st.v[m].x;
+                    ob[t + TPF * m] = st.v[m].y;
+                }
+            }
+        }
+    }
+};
+
+}  // namespace fcd

@@ -1,0 +1,194 @@
+// fcd_launch.cuh -- minimal runtime layer under the plan: device memory, copies and the
+// phase-kernel launcher.  Two builds of the same sources exist:
+//   * default (nvcc, sm_100a): real CUDA; this is the product (libfcd_b200.so).
+//   * -DFCD_EMULATE (g++): "device" memory is host memory and a launch runs every block,
+//     phase and thread sequentially on the CPU.  TEST INFRASTRUCTURE ONLY (tests/emul); it
+//     exists because the build container has no GPU.  The product never loads it.
+#pragma once
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#if !defined(FCD_EMULATE)
+#include <cuda_runtime.h>
+#endif
+
+namespace fcd {
+namespace rt {
+
+using stream_t = void*;
+
+[[noreturn]] inline void fail(const std::string& what) { throw std::runtime_error(what); }
+
+#if defined(FCD_EMULATE)
+// ------------------------------------------------------------------ CPU emulation --------
+inline void* dmalloc(size_t n) {
+    void* p = std::malloc(n ? n : 1);
+    if (!p) fail("emul: out of memory");
+    return p;
+}
+inline void dfree(void* p) { std::free(p); }
+inline void dmemset(void* p, int v, size_t n, stream_t) { std::memset(p, v, n); }
+inline void h2d(void* d, const void* h, size_t n, stream_t) { std::memcpy(d, h, n); }
+inline void d2h(void* h, const void* d, size_t n, stream_t) { std::memcpy(h, d, n); }
+inline void d2d(void* d, const void* s, size_t n, stream_t) { std::memmove(d, s, n); }
+inline void sync(stream_t) {}
+
+template <class K, int PH>
+inline void emu_phases(const typename K::Params& p, int bx, int by, unsigned char* smem, typename K::State* st) {
+    for (int tid = 0; tid < K::THREADS; ++tid) K::template phase<PH>(p, bx, by, tid, smem, st[tid]);
+    if constexpr (PH + 1 < K::PHASES) emu_phases<K, PH + 1>(p, bx, by, smem, st);
+}
+
+template <class K>
+inline void launch(int gx, int gy, stream_t, const typename K::Params& p) {
+    std::vector<unsigned char> smem((size_t)K::SMEM_BYTES + 16);
+    std::vector<typename K::State> st(K::THREADS);
+    for (int by = 0; by < gy; ++by)
+        for (int bx = 0; bx < gx; ++bx) emu_phases<K, 0>(p, bx, by, smem.data(), st.data());
+}
+
+#else
+// ------------------------------------------------------------------ CUDA -----------------
+inline void check(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) fail(std::string(what) + ": " + cudaGetErrorString(e));
+}
+inline void* dmalloc(size_t n) {
+    void* p = nullptr;
+    check(cudaMalloc(&p, n ? n : 1), "cudaMalloc");
+    return p;
+}
+inline void dfree(void* p) { if (p) cudaFree(p); }
+inline void dmemset(void* p, int v, size_t n, stream_t s) { check(cudaMemsetAsync(p, v, n, (cudaStream_t)s), "cudaMemsetAsync"); }
+inline void h2d(void* d, const void* h, size_t n, stream_t s) {
+    check(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, (cudaStream_t)s), "cudaMemcpyAsync h2d");
+    check(cudaStreamSynchronize((cudaStream_t)s), "sync after h2d");
+}
+inline void d2h(void* h, const void* d, size_t n, stream_t s) {
+    check(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, (cudaStream_t)s), "cudaMemcpyAsync d2h");
+    check(cudaStreamSynchronize((cudaStream_t)s), "sync after d2h");
+}
+inline void d2d(void* d, const void* s_, size_t n, stream_t s) {
+    check(cudaMemcpyAsync(d, s_, n, cudaMemcpyDeviceToDevice, (cudaStream_t)s), "cudaMemcpyAsync d2d");
+}
+inline void sync(stream_t s) { check(cudaStreamSynchronize((cudaStream_t)s), "cudaStreamSynchronize"); }
+
+template <class K, int PH>
+__device__ __forceinline__ void run_phases(const typename K::Params& p, unsigned char* smem, typename K::State& st) {
+    K::template phase<PH>(p, (int)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x, smem, st);
+    if constexpr (PH + 1 < K::PHASES) {
+        __syncthreads();
+        run_phases<K, PH + 1>(p, smem, st);
+    }
+}
+
+template <class K>
+__global__ void __launch_bounds__(K::THREADS) fcd_kernel(const __grid_constant__ typename K::Params p) {
+    extern __shared__ __align__(16) unsigned char fcd_smem[];
+    typename K::State st;
+    run_phases<K, 0>(p, fcd_smem, st);
+}
+
+template <class K>
+inline void launch(int gx, int gy, stream_t s, const typename K::Params& p) {
+    static bool configured = false;   // per kernel instantiation
+    if (!configured) {
+        if (K::SMEM_BYTES > 48 * 1024)
+            check(cudaFuncSetAttribute(fcd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES),
+                  "cudaFuncSetAttribute(smem)");
+        configured = true;
+    }
+    fcd_kernel<K><<<dim3((unsigned)gx, (unsigned)gy, 1), K::THREADS, K::SMEM_BYTES, (cudaStream_t)s>>>(p);
+    check(cudaGetLastError(), "kernel launch");
+}
+#endif
+
+// per-stage device timing with events recorded on the launch stream
+struct StageTimer {
+    static constexpr int kStages = 7;
+#if defined(FCD_EMULATE)
+    void reset() {}
+    void begin_chunk(stream_t, int) {}
+    void mark(stream_t, int) {}
+    void collect(double* ms, long long* launches, long long* frames) {
+        for (int i = 0; i < kStages; ++i) { ms[i] = 0; launches[i] = 0; frames[i] = 0; }
+    }
+#else
+    struct Rec { cudaEvent_t a, b; int stage, frames; };
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    std::vector<Rec> recs;
+    cudaEvent_t last = nullptr;
+    int cur_frames = 0;
+    double acc_ms[kStages] = {0};
+    long long acc_n[kStages] = {0}, acc_f[kStages] = {0};
+    cudaEvent_t get() {
+        if (used == pool.size()) {
+            cudaEvent_t e;
+            check(cudaEventCreate(&e), "cudaEventCreate");
+            pool.push_back(e);
+        }
+        return pool[used++];
+    }
+    void fold() {   // requires the stream to be idle
+        for (auto& r : recs) {
+            float ms = 0.f;
+            check(cudaEventElapsedTime(&ms, r.a, r.b), "cudaEventElapsedTime");
+            acc_ms[r.stage] += ms; acc_n[r.stage] += 1; acc_f[r.stage] += r.frames;
+        }
+        recs.clear();
+        used = 0;
+    }
+    void reset() {
+        recs.clear(); used = 0;
+        for (int i = 0; i < kStages; ++i) { acc_ms[i] = 0; acc_n[i] = 0; acc_f[i] = 0; }
+    }
+    void begin_chunk(stream_t s, int frames) {
+        if (used + 16 > 60000) { check(cudaStreamSynchronize((cudaStream_t)s), "sync"); fold(); }
+        last = get();
+        cur_frames = frames;
+        check(cudaEventRecord(last, (cudaStream_t)s), "cudaEventRecord");
+    }
+    void mark(stream_t s, int stage) {
+        cudaEvent_t e = get();
+        check(cudaEventRecord(e, (cudaStream_t)s), "cudaEventRecord");
+        recs.push_back(Rec{last, e, stage, cur_frames});
+        last = e;
+    }
+    void collect(double* ms, long long* launches, long long* frames) {
+        check(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+        fold();
+        for (int i = 0; i < kStages; ++i) { ms[i] = acc_ms[i]; launches[i] = acc_n[i]; frames[i] = acc_f[i]; }
+    }
+    ~StageTimer() { for (auto e : pool) cudaEventDestroy(e); }
+#endif
+};
+
+// typed device buffer with RAII
+template <class T>
+struct DevBuf {
+    T* ptr = nullptr;
+    size_t count = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { dfree(ptr); }
+    void alloc(size_t n) {
+        if (n == count && ptr) return;
+        dfree(ptr);
+        ptr = nullptr;
+        count = 0;
+        ptr = static_cast<T*>(dmalloc(n * sizeof(T)));
+        count = n;
+    }
+    void upload(const std::vector<T>& h, stream_t s) {
+        alloc(h.size());
+        h2d(ptr, h.data(), h.size() * sizeof(T), s);
+    }
+};
+
+}  // namespace rt
+}  // namespace fcd

@@ -1,0 +1,590 @@
+// fcd_plan.inl -- plan object and C ABI (include/fcd_b200.h).  Included by fcd_b200.cu
+// (CUDA, the product) and by tests/emul/fcd_emul.cpp (-DFCD_EMULATE, CPU emulation used
+// only by the CPU test-suite).  Host logic here mirrors, with citations, the scalar parts of
+// the reference: peak selection (pyfcd/fourier.py:25-41), disk chords (pyfcd/carriers.py:17-20),
+// carrier wavevectors (carriers.py:12), wavenumber vectors (fourier.py:44-57,76-92).
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <unordered_map>
+
+#include "fcd_b200.h"
+#include "fcd_generic.cuh"
+#include "fcd_launch.cuh"
+
+namespace fcd {
+
+// groups per block for each transform length (threads = G * L/16)
+template <int L> struct Tune;
+template <> struct Tune<64>   { static constexpr int GROW = 16, GCOL = 16, GDEM = 16, GGEN = 16; };
+template <> struct Tune<128>  { static constexpr int GROW = 8,  GCOL = 8,  GDEM = 8,  GGEN = 8; };
+template <> struct Tune<256>  { static constexpr int GROW = 8,  GCOL = 8,  GDEM = 8,  GGEN = 8; };
+template <> struct Tune<512>  { static constexpr int GROW = 4,  GCOL = 4,  GDEM = 4,  GGEN = 4; };
+template <> struct Tune<1024> { static constexpr int GROW = 4,  GCOL = 4,  GDEM = 4,  GGEN = 4; };
+template <> struct Tune<2048> { static constexpr int GROW = 2,  GCOL = 4,  GDEM = 2,  GGEN = 2; };
+template <> struct Tune<4096> { static constexpr int GROW = 2,  GCOL = 2,  GDEM = 2,  GGEN = 2; };
+
+#define FCD_CASE_L(N, ...) case N: { constexpr int L = N; __VA_ARGS__; } break;
+#define FCD_DISPATCH_L(value, ...)                                                      \
+    switch (value) {                                                                    \
+        FCD_CASE_L(64, __VA_ARGS__) FCD_CASE_L(128, __VA_ARGS__) FCD_CASE_L(256, __VA_ARGS__) \
+        FCD_CASE_L(512, __VA_ARGS__) FCD_CASE_L(1024, __VA_ARGS__) FCD_CASE_L(2048, __VA_ARGS__) \
+        FCD_CASE_L(4096, __VA_ARGS__)                                                   \
+        default: rt::fail("unsupported transform length");                              \
+    }
+
+static inline bool supported_dim(int n) { return n >= 64 && n <= 4096 && (n & (n - 1)) == 0; }
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// fftfreq(n, d)[j] as scipy computes it: integer * (1.0 / (n*d))          (fourier.py:56)
+static inline double fftfreq_at(int n, double d, int j) {
+    const double val = 1.0 / (n * d);
+    const int m = j < (n + 1) / 2 ? j : j - n;
+    return m * val;
+}
+// fftshift(fftfreq(n, d))[j]
+static inline double fftfreq_shifted_at(int n, double d, int j) { return fftfreq_at(n, d, (j + n - n / 2) % n); }
+
+struct PlanImpl {
+    int H = 0, W = 0, chunk = 1;
+    long long launches = 0;
+
+    rt::DevBuf<cf> tw_w_f, tw_h_f;
+    rt::DevBuf<cd> tw_w_d, tw_h_d;
+
+    // per-reference float64 scratch
+    rt::DevBuf<cd> spec, tmp;
+    rt::DevBuf<double> mag, kr_sq, kc_sq, sum;
+    rt::DevBuf<unsigned long long> maxbits;
+    rt::DevBuf<Candidate> cand;
+    rt::DevBuf<int> cand_count;
+    static constexpr int kCandCap = 1 << 18;
+
+    // bound reference
+    bool bound = false;
+    bool spec_valid = false;   // spec holds fft2(reference)
+    int peaks[4] = {0, 0, 0, 0};
+    double radius = 0, cal = 1, height = 1;
+    int c_lo[2] = {0, 0}, nc[2] = {0, 0}, ncp = 4;
+    std::vector<int> h_lo, h_hi;           // [2][ncp]
+    rt::DevBuf<int> chord_lo, chord_hi;
+    rt::DevBuf<cf> ccsgn;                  // [2][H][W]
+    rt::DevBuf<float> kx, kxq, ky, kyq;
+    double f[2][2] = {{0, 0}, {0, 0}};     // carrier wavevectors [k_row, k_col]
+    double det = 1;
+
+    // per-launch workspaces (chunk frames)
+    rt::DevBuf<cf> w1, w2, w3, w4;
+    rt::DevBuf<float> colphase, rowoff;
+    int w4p = 0;
+
+    template <class K>
+    void launch(int gx, int gy, rt::stream_t s, const typename K::Params& p) {
+        rt::launch<K>(gx, gy, s, p);
+        ++launches;
+    }
+
+    // optional per-stage device timing (CUDA events on the launch stream), for bench.py
+    static constexpr int kStages = 7;   // K1 K2 K3 K3b PhaseFix K4 K5
+    bool profiling = false;
+    rt::StageTimer timer;
+
+    // ------------------------------------------------------------------ construction ----
+    template <class T>
+    static std::vector<cx<T>> make_twiddles(int n) {
+        std::vector<cx<T>> t(n);
+        for (int j = 0; j < n; ++j) {
+            const long double a = -2.0L * 3.14159265358979323846264338327950288L * j / n;
+            t[j] = mk<T>((T)cosl(a), (T)sinl(a));
+        }
+        return t;
+    }
+
+    void init(int rows, int cols, int frames_per_launch) {
+        if (!supported_dim(rows) || !supported_dim(cols))
+            rt::fail("unsupported shape: rows and cols must be powers of two in [64, 4096]");
+        if (frames_per_launch < 1 || frames_per_launch > 16384) rt::fail("frames_per_launch out of range");
+        H = rows; W = cols; chunk = frames_per_launch;
+        tw_w_f.upload(make_twiddles<float>(W), nullptr);
+        tw_h_f.upload(make_twiddles<float>(H), nullptr);
+        tw_w_d.upload(make_twiddles<double>(W), nullptr);
+        tw_h_d.upload(make_twiddles<double>(H), nullptr);
+        w4p = W / 2 + 4;
+    }
+
+    void ensure_reference_scratch() {
+        const size_t n = (size_t)H * W;
+        spec.alloc(n);
+        tmp.alloc(n);
+    }
+
+    // ------------------------------------------------------------------ float64 fft2 ----
+    // out = fft2(in) (dir=-1) or ifft2(in) (dir=+1, scaled 1/(HW)); in may alias out for kind 0
+    void fft2_d(const void* in, int kind, double sub, cd* out, int dir, rt::stream_t s) {
+        FCD_DISPATCH_L(W, {
+            constexpr int G = Tune<L>::GGEN;
+            GenRowsParams<double> p{in, kind, sub, out, tw_w_d.ptr, H, 1.0};
+            if (dir < 0) launch<GenRows<L, G, -1, double>>(ceil_div(H, G), 1, s, p);
+            else launch<GenRows<L, G, +1, double>>(ceil_div(H, G), 1, s, p);
+        })
+        FCD_DISPATCH_L(H, {
+            constexpr int G = Tune<L>::GGEN;
+            GenColsParams<double> p{out, out, tw_h_d.ptr, W, dir < 0 ? 1.0 : 1.0 / ((double)H * W)};
+            if (dir < 0) launch<GenCols<L, G, -1, double>>(ceil_div(W, G), 1, s, p);
+            else launch<GenCols<L, G, +1, double>>(ceil_div(W, G), 1, s, p);
+        })
+    }
+
+    static int elem_blocks(long long n) { return (int)std::min<long long>((n + 255) / 256, 148 * 8); }
+
+    // ------------------------------------------------------------------ carrier search ----
+    double highpass_spectrum(const void* image, int is_f64, double* spectrum_out, rt::stream_t s) {
+        ensure_reference_scratch();
+        const long long n = (long long)H * W;
+        mag.alloc(n);
+        sum.alloc(1);
+        maxbits.alloc(1);
+        rt::dmemset(sum.ptr, 0, sizeof(double), s);
+        rt::dmemset(maxbits.ptr, 0, sizeof(unsigned long long), s);
+        const int nb = elem_blocks(n);
+        launch<SumKernel>(nb, 1, s, SumParams{image, is_f64, n, sum.ptr, nb});
+        double total = 0;
+        rt::d2h(&total, sum.ptr, sizeof(double), s);
+        const double mean = total / (double)n;                      // image - np.mean(image), fourier.py:18
+        fft2_d(image, is_f64 ? 2 : 1, mean, spec.ptr, -1, s);
+        spec_valid = false;
+        if (kr_sq.count != (size_t)H || kc_sq.count != (size_t)W) {
+            const double d = 1.0 / (2.0 * M_PI);                    // wavenumber(size, 1, shifted=True)
+            std::vector<double> a(H), b(W);
+            for (int j = 0; j < H; ++j) { const double k = fftfreq_shifted_at(H, d, j); a[j] = k * k; }
+            for (int j = 0; j < W; ++j) { const double k = fftfreq_shifted_at(W, d, j); b[j] = k * k; }
+            kr_sq.upload(a, s);
+            kc_sq.upload(b, s);
+        }
+        const double kmin = 4.0 * M_PI / std::min(H, W);            // fourier.py:22
+        launch<SpecMag>(nb, 1, s, SpecMagParams{spec.ptr, spectrum_out ? spectrum_out : mag.ptr, kr_sq.ptr,
+                                                  kc_sq.ptr, kmin * kmin, maxbits.ptr, H, W, nb});
+        if (spectrum_out) rt::d2d(mag.ptr, spectrum_out, n * sizeof(double), s);
+        unsigned long long bits = 0;
+        rt::d2h(&bits, maxbits.ptr, sizeof(bits), s);
+        double mx;
+        std::memcpy(&mx, &bits, sizeof(mx));
+        return mx;
+    }
+
+    std::vector<std::array<int, 2>> peak_locations(const double* image, double threshold, int max_peaks,
+                                                   rt::stream_t s) {
+        const long long n = (long long)H * W;
+        cand.alloc(kCandCap);
+        cand_count.alloc(1);
+        rt::dmemset(cand_count.ptr, 0, sizeof(int), s);
+        const int nb = elem_blocks(n);
+        launch<Candidates>(nb, 1, s, CandidatesParams{image, threshold, cand.ptr, cand_count.ptr, kCandCap, H, W, nb});
+        int count = 0;
+        rt::d2h(&count, cand_count.ptr, sizeof(int), s);
+        if (count > kCandCap) rt::fail("too many pixels above the peak threshold (flat spectrum?)");
+        std::vector<Candidate> c((size_t)count);
+        if (count) rt::d2h(c.data(), cand.ptr, sizeof(Candidate) * (size_t)count, s);
+        // raster order, then 8-connected labelling numbered by first pixel (skimage.measure.label)
+        std::sort(c.begin(), c.end(), [](const Candidate& a, const Candidate& b) {
+            return a.r != b.r ? a.r < b.r : a.c < b.c;
+        });
+        std::unordered_map<long long, int> at;
+        at.reserve(c.size() * 2 + 1);
+        for (int i = 0; i < count; ++i) at[(long long)c[i].r * W + c[i].c] = i;
+        std::vector<int> lab((size_t)count, -1);
+        int nlab = 0;
+        std::vector<int> stack;
+        for (int i = 0; i < count; ++i) {
+            if (lab[i] >= 0) continue;
+            lab[i] = nlab;
+            stack.push_back(i);
+            while (!stack.empty()) {
+                const int j = stack.back();
+                stack.pop_back();
+                for (int dr = -1; dr <= 1; ++dr)
+                    for (int dc = -1; dc <= 1; ++dc) {
+                        auto it = at.find((long long)(c[j].r + dr) * W + (c[j].c + dc));
+                        if (it != at.end() && c[j].c + dc >= 0 && c[j].c + dc < W && lab[it->second] < 0) {
+                            lab[it->second] = nlab;
+                            stack.push_back(it->second);
+                        }
+                    }
+            }
+            ++nlab;
+        }
+        struct Blob { double v; int r, c; };
+        std::vector<Blob> blobs((size_t)nlab, Blob{-1.0, 0, 0});
+        for (int i = 0; i < count; ++i) {      // raster order within a blob: first maximum wins
+            Blob& b = blobs[lab[i]];
+            if (c[i].v > b.v) b = Blob{c[i].v, c[i].r, c[i].c};
+        }
+        std::stable_sort(blobs.begin(), blobs.end(), [](const Blob& a, const Blob& b) { return a.v < b.v; });
+        std::vector<std::array<int, 2>> out;
+        for (int i = 0; i < nlab && i < max_peaks; ++i) out.push_back({blobs[i].r, blobs[i].c});
+        return out;
+    }
+
+    // fourier.find_peaks: fourier.py:25-41
+    void find_peaks(const void* image, int is_f64, int out[4], rt::stream_t s) {
+        const double mx = highpass_spectrum(image, is_f64, nullptr, s);
+        auto locs = peak_locations(mag.ptr, 0.5 * mx, 4, s);
+        if (locs.empty()) throw std::domain_error("no carrier peak above threshold");
+        const double d = 1.0 / (2.0 * M_PI);
+        auto kof = [&](const std::array<int, 2>& p, double k[2]) {
+            k[0] = fftfreq_shifted_at(H, d, p[0]);
+            k[1] = fftfreq_shifted_at(W, d, p[1]);
+        };
+        int best = 0;
+        double bestv = 0;
+        for (size_t i = 0; i < locs.size(); ++i) {
+            double k[2];
+            kof(locs[i], k);
+            const double v = std::fabs(std::atan2(k[0], k[1]));
+            if (i == 0 || v < bestv) { best = (int)i; bestv = v; }
+        }
+        double k1[2];
+        kof(locs[best], k1);
+        int perp = 0;
+        double perpv = 0;
+        for (size_t i = 0; i < locs.size(); ++i) {
+            double k[2];
+            kof(locs[i], k);
+            const double v = std::fabs(k1[0] * k[0] + k1[1] * k[1]);
+            if (i == 0 || v < perpv) { perp = (int)i; perpv = v; }
+        }
+        out[0] = locs[best][0]; out[1] = locs[best][1];
+        out[2] = locs[perp][0]; out[3] = locs[perp][1];
+    }
+
+    // ------------------------------------------------------------------ bind ----
+    void compute_chords() {
+        // disk ((r-r0)/R)^2 + ((c-c0)/R)^2 < 1 on the shifted grid, clipped to the array
+        std::vector<int> lo[2], hi[2];
+        for (int i = 0; i < 2; ++i) {
+            const double r0 = peaks[2 * i], c0 = peaks[2 * i + 1];
+            int first = -1, last = -1;
+            std::vector<int> clo(W, 1), chi(W, 0);
+            for (int c = 0; c < W; ++c) {
+                const double dc = (c - c0) / radius;
+                if (!(dc * dc < 1.0)) continue;
+                int rlo = -1, rhi = -1;
+                const int ra = std::max(0, (int)std::floor(r0 - radius) - 1);
+                const int rb = std::min(H - 1, (int)std::ceil(r0 + radius) + 1);
+                for (int r = ra; r <= rb; ++r) {
+                    const double dr = (r - r0) / radius;
+                    if (dr * dr + dc * dc < 1.0) { if (rlo < 0) rlo = r; rhi = r; }
+                }
+                if (rlo >= 0) {
+                    clo[c] = rlo; chi[c] = rhi;
+                    if (first < 0) first = c;
+                    last = c;
+                }
+            }
+            if (first < 0) { first = 0; last = -1; }
+            c_lo[i] = first;
+            nc[i] = last - first + 1;
+            lo[i].assign(clo.begin() + first, clo.begin() + first + nc[i]);
+            hi[i].assign(chi.begin() + first, chi.begin() + first + nc[i]);
+        }
+        ncp = std::max(4, (std::max(nc[0], nc[1]) + 3) / 4 * 4);
+        h_lo.assign((size_t)2 * ncp, 1);
+        h_hi.assign((size_t)2 * ncp, 0);
+        for (int i = 0; i < 2; ++i)
+            for (int c = 0; c < nc[i]; ++c) { h_lo[(size_t)i * ncp + c] = lo[i][c]; h_hi[(size_t)i * ncp + c] = hi[i][c]; }
+    }
+
+    void masked_inverse(int i, rt::stream_t s, uint8_t* mask_out) {
+        // tmp = ifft2(spec * mask_i)
+        const long long n = (long long)H * W;
+        const int nb = elem_blocks(n);
+        launch<MaskMul>(nb, 1, s, MaskMulParams{spec.ptr, mask_out ? nullptr : tmp.ptr, chord_lo.ptr + (size_t)i * ncp,
+                                                  chord_hi.ptr + (size_t)i * ncp, c_lo[i], nc[i], H, W, nb, mask_out});
+        if (!mask_out) fft2_d(tmp.ptr, 0, 0.0, tmp.ptr, +1, s);
+    }
+
+    void set_height(double h) {
+        if (!(h != 0.0)) rt::fail("height must be non-zero");
+        height = h;
+    }
+
+    void bind(const void* ref, int is_f64, const int pk[4], double rad, double calib, double h, rt::stream_t s) {
+        if (!(rad > 0.0)) rt::fail("carrier radius must be positive");
+        if (!(calib > 0.0)) rt::fail("calibration factor must be positive");
+        for (int i = 0; i < 4; ++i) {
+            const int lim = (i % 2 == 0) ? H : W;
+            if (pk[i] < 0 || pk[i] >= lim) rt::fail("carrier peak outside the spectrum");
+            peaks[i] = pk[i];
+        }
+        radius = rad; cal = calib;
+        set_height(h);
+        bound = false;
+        ensure_reference_scratch();
+        compute_chords();
+        if (nc[0] <= 0 || nc[1] <= 0) rt::fail("empty carrier disk");
+        chord_lo.upload(h_lo, s);
+        chord_hi.upload(h_hi, s);
+
+        // carrier wavevectors: pixel_to_wavenumber(shape, peak, cal)   (carriers.py:12)
+        const double d = cal / (2.0 * M_PI);
+        for (int i = 0; i < 2; ++i) {
+            f[i][0] = fftfreq_shifted_at(H, d, peaks[2 * i]);
+            f[i][1] = fftfreq_shifted_at(W, d, peaks[2 * i + 1]);
+        }
+        det = f[0][1] * f[1][0] - f[0][0] * f[1][1];                 // fcd.py:134-135
+
+        // wavenumber vectors of integrate_in_fourier with the N//2+1 quirk (fourier.py:128-132)
+        std::vector<float> vkx(W), vkxq(W), vky(H), vkyq(H);
+        for (int j = 0; j < W; ++j) { vkx[j] = (float)fftfreq_at(W, d, j); vkxq[j] = vkx[j]; }
+        for (int j = 0; j < H; ++j) { vky[j] = (float)fftfreq_at(H, d, j); vkyq[j] = vky[j]; }
+        vkxq[W / 2 + 1] = 0.f;
+        vkyq[H / 2 + 1] = 0.f;
+        kx.upload(vkx, s); kxq.upload(vkxq, s); ky.upload(vky, s); kyq.upload(vkyq, s);
+
+        // ccsgn_i = conj(ifft2(fft2(ref) * mask_i))   (carriers.py:22-24), float64 then stored c64
+        fft2_d(ref, is_f64 ? 2 : 1, 0.0, spec.ptr, -1, s);
+        spec_valid = true;
+        const long long n = (long long)H * W;
+        ccsgn.alloc((size_t)2 * n);
+        for (int i = 0; i < 2; ++i) {
+            masked_inverse(i, s, nullptr);
+            const int nb = elem_blocks(n);
+            launch<CcsgnStore>(nb, 1, s, CcsgnStoreParams{tmp.ptr, ccsgn.ptr + (size_t)i * n, nullptr, n, nb});
+        }
+
+        // workspaces
+        w1.alloc((size_t)chunk * 2 * ncp * H);
+        w2.alloc((size_t)chunk * 2 * ncp * H);
+        w3.alloc((size_t)chunk * n);
+        w4.alloc((size_t)chunk * H * w4p);
+        colphase.alloc((size_t)chunk * 2 * H);
+        rowoff.alloc((size_t)chunk * 2 * H);
+        rt::sync(s);
+        bound = true;
+    }
+
+    // ------------------------------------------------------------------ execute ----
+    void execute(const float* frames, int n_frames, float* height_out, float* phases, const uint8_t* mask,
+                 long long mask_stride, int unwrap, rt::stream_t s) {
+        if (!bound) throw std::logic_error("fcd_execute called before fcd_bind_reference");
+        if (n_frames < 0) rt::fail("negative frame count");
+        if (det == 0.0) rt::fail("carriers are collinear (singular 2x2 system)");
+        const long long n = (long long)H * W;
+        const float scale_demod = (float)(1.0 / (2.0 * (double)H * (double)W));
+        const float scale_int = (float)(1.0 / (2.0 * height * det * (double)H * (double)W));
+        for (int f0 = 0; f0 < n_frames; f0 += chunk) {
+            const int nf = std::min(chunk, n_frames - f0);
+            const float* fr = frames + (long long)f0 * n;
+            float* ho = height_out + (long long)f0 * n;
+            float* po = phases ? phases + (long long)f0 * 2 * n : nullptr;
+            const uint8_t* mk_ = mask ? mask + (long long)f0 * mask_stride : nullptr;
+            if (profiling) timer.begin_chunk(s, nf);
+            FCD_DISPATCH_L(W, {
+                constexpr int G = Tune<L>::GROW;
+                RowFwdParams p{fr, nullptr, mk_, mask_stride, w1.ptr, tw_w_f.ptr, H, ncp,
+                               {nc[0], nc[1]}, {c_lo[0] - W / 2, c_lo[1] - W / 2}};
+                p.reference = reference_f32();
+                launch<RowFwd<L, G>>(H / (2 * G), nf, s, p);
+            })
+            if (profiling) timer.mark(s, 0);
+            FCD_DISPATCH_L(H, {
+                constexpr int G = Tune<L>::GCOL;
+                ColBandParams p{w1.ptr, w2.ptr, tw_h_f.ptr, chord_lo.ptr, chord_hi.ptr, ncp, {nc[0], nc[1]}, scale_demod};
+                launch<ColBand<L, G>>(ceil_div(ncp, G), nf * 2, s, p);
+            })
+            if (profiling) timer.mark(s, 1);
+            FCD_DISPATCH_L(W, {
+                constexpr int G = Tune<L>::GDEM;
+                RowDemodParams p{w2.ptr, ccsgn.ptr, w3.ptr, colphase.ptr, po, tw_w_f.ptr, H, ncp,
+                                 {nc[0], nc[1]}, {c_lo[0] - W / 2, c_lo[1] - W / 2}, W / 2, unwrap ? 1 : 0};
+                launch<RowDemod<L, G>>(H / G, nf, s, p);
+            })
+            if (profiling) timer.mark(s, 2);
+            launch<RowLink>(2, nf, s, RowLinkParams{colphase.ptr, rowoff.ptr, H, H / 2, unwrap ? 1 : 0});
+            if (profiling) timer.mark(s, 3);
+            if (po && unwrap) {
+                launch<PhaseFix>(H, nf * 2, s, PhaseFixParams{po, rowoff.ptr, H, W});
+                if (profiling) timer.mark(s, 4);
+            }
+            FCD_DISPATCH_L(H, {
+                constexpr int G = Tune<L>::GCOL;
+                ColIntegrateParams p{w3.ptr, rowoff.ptr, w4.ptr, tw_h_f.ptr, kx.ptr, kxq.ptr, ky.ptr, kyq.ptr, W, w4p,
+                                     (float)f[0][0], (float)f[0][1], (float)f[1][0], (float)f[1][1], scale_int,
+                                     unwrap ? 1 : 0};
+                launch<ColIntegrate<L, G>>(ceil_div(W / 2 + 1, G), nf, s, p);
+            })
+            if (profiling) timer.mark(s, 5);
+            FCD_DISPATCH_L(W, {
+                constexpr int G = Tune<L>::GROW;
+                RowInvParams p{w4.ptr, ho, mk_, mask_stride, tw_w_f.ptr, H, w4p};
+                launch<RowInv<L, G>>(H / (2 * G), nf, s, p);
+            })
+            if (profiling) timer.mark(s, 6);
+        }
+    }
+
+    // float32 copy of the reference for mask substitution (analyze.py:231), made on demand
+    rt::DevBuf<float> ref_f32;
+    bool ref_f32_valid = false;
+    const float* reference_f32() const { return ref_f32_valid ? ref_f32.ptr : nullptr; }
+};
+
+}  // namespace fcd
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+struct fcd_plan {
+    fcd::PlanImpl impl;
+};
+
+static thread_local std::string g_fcd_error;
+
+template <class Fn>
+static int fcd_guard(Fn&& fn) {
+    try {
+        fn();
+        return FCD_OK;
+    } catch (const std::domain_error& e) {
+        g_fcd_error = e.what();
+        return FCD_ERR_NOPEAKS;
+    } catch (const std::logic_error& e) {
+        g_fcd_error = e.what();
+        return FCD_ERR_STATE;
+    } catch (const std::runtime_error& e) {
+        g_fcd_error = e.what();
+        const bool cuda = g_fcd_error.find("cuda") != std::string::npos || g_fcd_error.find("kernel launch") != std::string::npos;
+        return cuda ? FCD_ERR_RUNTIME : FCD_ERR_INVALID;
+    } catch (const std::exception& e) {
+        g_fcd_error = e.what();
+        return FCD_ERR_RUNTIME;
+    }
+}
+
+extern "C" {
+
+const char* fcd_last_error(void) { return g_fcd_error.c_str(); }
+
+int fcd_plan_create(int rows, int cols, int frames_per_launch, fcd_plan** out) {
+    if (!out) { g_fcd_error = "null output pointer"; return FCD_ERR_INVALID; }
+    *out = nullptr;
+    return fcd_guard([&] {
+        fcd_plan* p = new fcd_plan();
+        try {
+            p->impl.init(rows, cols, frames_per_launch);
+        } catch (...) {
+            delete p;
+            throw;
+        }
+        *out = p;
+    });
+}
+
+int fcd_plan_destroy(fcd_plan* plan) {
+    delete plan;
+    return FCD_OK;
+}
+
+int fcd_highpass_spectrum(fcd_plan* plan, const void* image_dev, int image_is_f64, double* spectrum_dev,
+                          double* max_out, void* stream) {
+    if (!plan || !image_dev) { g_fcd_error = "null argument"; return FCD_ERR_INVALID; }
+    return fcd_guard([&] {
+        const double mx = plan->impl.highpass_spectrum(image_dev, image_is_f64, spectrum_dev, stream);
+        if (max_out) *max_out = mx;
+    });
+}
+
+int fcd_peak_locations(fcd_plan* plan, const double* image_dev, double threshold, int max_peaks, int* rc_out,
+                       int* count_out, void* stream) {
+    if (!plan || !image_dev || !rc_out || !count_out || max_peaks < 0) { g_fcd_error = "bad argument"; return FCD_ERR_INVALID; }
+    return fcd_guard([&] {
+        auto v = plan->impl.peak_locations(image_dev, threshold, max_peaks, stream);
+        *count_out = (int)v.size();
+        for (size_t i = 0; i < v.size(); ++i) { rc_out[2 * i] = v[i][0]; rc_out[2 * i + 1] = v[i][1]; }
+    });
+}
+
+int fcd_find_peaks(fcd_plan* plan, const void* image_dev, int image_is_f64, int peaks_out[4], void* stream) {
+    if (!plan || !image_dev || !peaks_out) { g_fcd_error = "null argument"; return FCD_ERR_INVALID; }
+    return fcd_guard([&] { plan->impl.find_peaks(image_dev, image_is_f64, peaks_out, stream); });
+}
+
+int fcd_bind_reference(fcd_plan* plan, const void* reference_dev, int reference_is_f64, const int peaks[4],
+                       double radius, double calibration_factor, double height, void* stream) {
+    if (!plan || !reference_dev || !peaks) { g_fcd_error = "null argument"; return FCD_ERR_INVALID; }
+    return fcd_guard([&] {
+        auto& im = plan->impl;
+        im.bind(reference_dev, reference_is_f64, peaks, radius, calibration_factor, height, stream);
+        // float32 copy of the reference for the masked workflow
+        const long long n = (long long)im.H * im.W;
+        im.ref_f32.alloc((size_t)n);
+        if (!reference_is_f64) {
+            fcd::rt::d2d(im.ref_f32.ptr, reference_dev, n * sizeof(float), stream);
+            fcd::rt::sync(stream);
+            im.ref_f32_valid = true;
+        } else {
+            std::vector<double> h((size_t)n);
+            fcd::rt::d2h(h.data(), reference_dev, n * sizeof(double), stream);
+            std::vector<float> hf((size_t)n);
+            for (long long i = 0; i < n; ++i) hf[i] = (float)h[i];
+            fcd::rt::h2d(im.ref_f32.ptr, hf.data(), n * sizeof(float), stream);
+            im.ref_f32_valid = true;
+        }
+    });
+}
+
+int fcd_execute(fcd_plan* plan, const float* frames_dev, int n_frames, float* height_dev, float* phases_dev,
+                const uint8_t* mask_dev, long long mask_stride, int unwrap, void* stream) {
+    if (!plan || (n_frames > 0 && (!frames_dev || !height_dev))) { g_fcd_error = "null argument"; return FCD_ERR_INVALID; }
+    return fcd_guard([&] {
+        plan->impl.execute(frames_dev, n_frames, height_dev, phases_dev, mask_dev, mask_stride, unwrap, stream);
+    });
+}
+
+int fcd_get_carrier_mask(fcd_plan* plan, int carrier, uint8_t* mask_dev, void* stream) {
+    if (!plan || !mask_dev || carrier < 0 || carrier > 1) { g_fcd_error = "bad argument"; return FCD_ERR_INVALID; }
+    return fcd_guard([&] {
+        if (!plan->impl.bound) throw std::logic_error("no reference bound");
+        plan->impl.masked_inverse(carrier, stream, mask_dev);
+    });
+}
+
+int fcd_get_carrier_ccsgn(fcd_plan* plan, int carrier, void* ccsgn_dev, int as_c128, void* stream) {
+    if (!plan || !ccsgn_dev || carrier < 0 || carrier > 1) { g_fcd_error = "bad argument"; return FCD_ERR_INVALID; }
+    return fcd_guard([&] {
+        auto& im = plan->impl;
+        if (!im.bound || !im.spec_valid) throw std::logic_error("no reference bound");
+        const long long n = (long long)im.H * im.W;
+        if (!as_c128) {
+            fcd::rt::d2d(ccsgn_dev, im.ccsgn.ptr + (size_t)carrier * n, n * sizeof(fcd::cf), stream);
+            return;
+        }
+        im.masked_inverse(carrier, stream, nullptr);
+        const int nb = fcd::PlanImpl::elem_blocks(n);
+        im.launch<fcd::CcsgnStore>(nb, 1, stream,
+                                   fcd::CcsgnStoreParams{im.tmp.ptr, nullptr, static_cast<fcd::cd*>(ccsgn_dev), n, nb});
+    });
+}
+
+int fcd_fft2_c128(fcd_plan* plan, const void* in_dev, void* out_dev, int direction, void* stream) {
+    if (!plan || !in_dev || !out_dev || (direction != 1 && direction != -1)) { g_fcd_error = "bad argument"; return FCD_ERR_INVALID; }
+    return fcd_guard([&] { plan->impl.fft2_d(in_dev, 0, 0.0, static_cast<fcd::cd*>(out_dev), direction, stream); });
+}
+
+int fcd_set_profiling(fcd_plan* plan, int enable) {
+    if (!plan) { g_fcd_error = "null plan"; return FCD_ERR_INVALID; }
+    return fcd_guard([&] {
+        plan->impl.profiling = enable != 0;
+        plan->impl.timer.reset();
+    });
+}
+
+int fcd_stage_times(fcd_plan* plan, double ms_out[7], long long launches_out[7], long long frames_out[7]) {
+    if (!plan || !ms_out || !launches_out || !frames_out) { g_fcd_error = "null argument"; return FCD_ERR_INVALID; }
+    return fcd_guard([&] { plan->impl.timer.collect(ms_out, launches_out, frames_out); });
+}
+
+long long fcd_launch_count(const fcd_plan* plan) { return plan ? plan->impl.launches : 0; }
+int fcd_band_columns(const fcd_plan* plan) { return plan ? plan->impl.ncp : 0; }
+
+}  // extern "C"

@@ -1,0 +1,225 @@
+// fft_core.cuh -- register/shared-memory Stockham FFT building blocks for sm_100a.
+//
+// Every transform in the FCD path is a complex FFT of one image row or column
+// (length L = 64..4096, power of two).  L/16 threads cooperate on one transform; each
+// thread owns the 16 elements  x[t + (L/16)*m], m = 0..15  both BEFORE and AFTER the
+// transform ("natural strided ownership").  Consecutive threads therefore touch
+// consecutive addresses, so the first pass can be fed straight from coalesced global
+// loads and the last pass can feed coalesced global stores; only the two inter-pass
+// exchanges go through shared memory (one padded buffer of L + L/16 elements).
+//
+// The transform is a decimation-in-time Stockham autosort in up to three passes of radix
+// R1*R2*R3 = L (each radix in {2,4,8,16}; R2 = 1 means two passes).  A pass of radix R < 16
+// runs 16/R butterflies per thread.  Pass structure (P = product of the previous radices):
+//     butterfly i in [0, L/R):  k = i mod P
+//        u[a] = x[i + a*L/R] * W_{P*R}^{k*a}          a = 0..R-1      (read, conflict free)
+//        u    = DFT_R(u)
+//        y[(i-k)*R + k + a*P] = u[a]                                   (write, padded)
+// The code is __host__ __device__ so that tests/emul can execute exactly the same
+// arithmetic and index maps on the CPU (this container has no GPU).
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define FCD_HD __host__ __device__ __forceinline__
+#define FCD_UNROLL _Pragma("unroll")
+#else
+#define FCD_HD inline
+#define FCD_UNROLL
+#endif
+
+namespace fcd {
+
+template <class T>
+struct alignas(2 * sizeof(T)) cx {
+    T x, y;
+};
+using cf = cx<float>;
+using cd = cx<double>;
+
+template <class T> FCD_HD cx<T> mk(T a, T b) { cx<T> r; r.x = a; r.y = b; return r; }
+template <class T> FCD_HD cx<T> operator+(cx<T> a, cx<T> b) { return mk<T>(a.x + b.x, a.y + b.y); }
+template <class T> FCD_HD cx<T> operator-(cx<T> a, cx<T> b) { return mk<T>(a.x - b.x, a.y - b.y); }
+template <class T> FCD_HD cx<T> operator*(cx<T> a, cx<T> b) {
+    return mk<T>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+template <class T> FCD_HD cx<T> conj(cx<T> a) { return mk<T>(a.x, -a.y); }
+template <class T> FCD_HD cx<T> scale(cx<T> a, T s) { return mk<T>(a.x * s, a.y * s); }
+// multiply by +i / -i
+template <class T> FCD_HD cx<T> mul_pi(cx<T> a) { return mk<T>(-a.y, a.x); }
+template <class T> FCD_HD cx<T> mul_mi(cx<T> a) { return mk<T>(a.y, -a.x); }
+// multiply by exp(DIR * i * angle) given (c, s) = (cos, sin) of the positive angle
+template <int DIR, class T> FCD_HD cx<T> rot(cx<T> a, T c, T s) {
+    return DIR < 0 ? mk<T>(a.x * c + a.y * s, a.y * c - a.x * s) : mk<T>(a.x * c - a.y * s, a.y * c + a.x * s);
+}
+template <int DIR, class T> FCD_HD cx<T> mul_dir_i(cx<T> a) { return DIR < 0 ? mul_mi(a) : mul_pi(a); }
+
+// ---------------------------------------------------------------------------------------
+// in-register DFTs on strided slots v[0], v[S], ..., natural order in and out.
+// DIR = -1: forward (exp(-2 pi i nk/R)); DIR = +1: inverse (unnormalised).
+// ---------------------------------------------------------------------------------------
+template <int DIR, class T> FCD_HD void dft2(cx<T>& a, cx<T>& b) {
+    cx<T> t = a - b;
+    a = a + b;
+    b = t;
+}
+
+template <int DIR, class T> FCD_HD void dft4(cx<T>& a0, cx<T>& a1, cx<T>& a2, cx<T>& a3) {
+    cx<T> t0 = a0 + a2, t1 = a0 - a2, t2 = a1 + a3, t3 = mul_dir_i<DIR>(a1 - a3);
+    a0 = t0 + t2;
+    a2 = t0 - t2;
+    a1 = t1 + t3;
+    a3 = t1 - t3;
+}
+
+template <int R, int S, int DIR, class T> struct Dft;
+
+template <int S, int DIR, class T> struct Dft<2, S, DIR, T> {
+    FCD_HD static void run(cx<T>* v) { dft2<DIR>(v[0], v[S]); }
+};
+template <int S, int DIR, class T> struct Dft<4, S, DIR, T> {
+    FCD_HD static void run(cx<T>* v) { dft4<DIR>(v[0], v[S], v[2 * S], v[3 * S]); }
+};
+template <int S, int DIR, class T> struct Dft<8, S, DIR, T> {
+    // n = 4*n1 + n2, k = k1 + 2*k2
+    FCD_HD static void run(cx<T>* v) {
+        const T h = T(0.70710678118654752440);
+        cx<T> y0[4], y1[4];
+        FCD_UNROLL
+        for (int n2 = 0; n2 < 4; ++n2) {
+            y0[n2] = v[n2 * S] + v[(n2 + 4) * S];
+            y1[n2] = v[n2 * S] - v[(n2 + 4) * S];
+        }
+        y1[1] = rot<DIR>(y1[1], h, h);
+        y1[2] = mul_dir_i<DIR>(y1[2]);
+        y1[3] = rot<DIR>(y1[3], -h, h);
+        dft4<DIR>(y0[0], y0[1], y0[2], y0[3]);
+        dft4<DIR>(y1[0], y1[1], y1[2], y1[3]);
+        FCD_UNROLL
+        for (int k2 = 0; k2 < 4; ++k2) {
+            v[(2 * k2) * S] = y0[k2];
+            v[(2 * k2 + 1) * S] = y1[k2];
+        }
+    }
+};
+template <int S, int DIR, class T> struct Dft<16, S, DIR, T> {
+    // n = 4*n1 + n2, k = k1 + 4*k2
+    FCD_HD static void run(cx<T>* v) {
+        const T c1 = T(0.92387953251128675613), s1 = T(0.38268343236508977173);
+        const T h = T(0.70710678118654752440);
+        cx<T> y[4][4];  // y[k1][n2]
+        FCD_UNROLL
+        for (int n2 = 0; n2 < 4; ++n2) {
+            cx<T> a0 = v[n2 * S], a1 = v[(4 + n2) * S], a2 = v[(8 + n2) * S], a3 = v[(12 + n2) * S];
+            dft4<DIR>(a0, a1, a2, a3);
+            y[0][n2] = a0; y[1][n2] = a1; y[2][n2] = a2; y[3][n2] = a3;
+        }
+        // twiddles W16^(n2*k1)
+        y[1][1] = rot<DIR>(y[1][1], c1, s1);
+        y[1][2] = rot<DIR>(y[1][2], h, h);
+        y[1][3] = rot<DIR>(y[1][3], s1, c1);
+        y[2][1] = rot<DIR>(y[2][1], h, h);
+        y[2][2] = mul_dir_i<DIR>(y[2][2]);
+        y[2][3] = rot<DIR>(y[2][3], -h, h);
+        y[3][1] = rot<DIR>(y[3][1], s1, c1);
+        y[3][2] = rot<DIR>(y[3][2], -h, h);
+        y[3][3] = rot<DIR>(y[3][3], -c1, -s1);
+        FCD_UNROLL
+        for (int k1 = 0; k1 < 4; ++k1) {
+            dft4<DIR>(y[k1][0], y[k1][1], y[k1][2], y[k1][3]);
+            FCD_UNROLL
+            for (int k2 = 0; k2 < 4; ++k2) v[(k1 + 4 * k2) * S] = y[k1][k2];
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// radix plans
+// ---------------------------------------------------------------------------------------
+template <int L> struct Plan;
+template <> struct Plan<64>   { static constexpr int R1 = 4,  R2 = 1,  R3 = 16; };
+template <> struct Plan<128>  { static constexpr int R1 = 8,  R2 = 1,  R3 = 16; };
+template <> struct Plan<256>  { static constexpr int R1 = 16, R2 = 1,  R3 = 16; };
+template <> struct Plan<512>  { static constexpr int R1 = 8,  R2 = 8,  R3 = 8; };
+template <> struct Plan<1024> { static constexpr int R1 = 8,  R2 = 8,  R3 = 16; };
+template <> struct Plan<2048> { static constexpr int R1 = 8,  R2 = 16, R3 = 16; };
+template <> struct Plan<4096> { static constexpr int R1 = 16, R2 = 16, R3 = 16; };
+
+// smem slot of logical element p: one pad element per 16 (keeps radix-strided writes of
+// the first pass and 16-aligned runs of the later passes bank-conflict free)
+FCD_HD int fft_pos(int p) { return p + (p >> 4); }
+
+template <int L, int DIR, class T, class P = Plan<L>>
+struct Fft {
+    static constexpr int R1 = P::R1, R2 = P::R2, R3 = P::R3;
+    static_assert(R1 * R2 * R3 == L, "radix plan must multiply to L");
+    static constexpr int TPF = L / 16;         // threads per transform
+    static constexpr int SMEM = L + L / 16;    // elements of the padded exchange buffer
+    static constexpr bool THREE = (R2 != 1);
+
+    // twiddle W_L^n (table holds exp(-2 pi i n / L)); DIR=+1 conjugates
+    FCD_HD static cx<T> tw(const cx<T>* __restrict__ table, int n) {
+        cx<T> w = table[n];
+        return DIR < 0 ? w : conj(w);
+    }
+
+    // gather butterfly inputs of a pass with radix R and prior product PP; apply twiddles
+    template <int R, int PP>
+    FCD_HD static void gather(cx<T>* v, int t, const cx<T>* s, const cx<T>* __restrict__ table) {
+        constexpr int NB = 16 / R;
+        FCD_UNROLL
+        for (int ii = 0; ii < NB; ++ii) {
+            const int i = t + TPF * ii;
+            const int k = i & (PP - 1);
+            FCD_UNROLL
+            for (int a = 0; a < R; ++a) {
+                cx<T> val = s[fft_pos(i + a * (L / R))];
+                if (PP > 1 && a > 0) val = val * tw(table, (L / (PP * R)) * k * a);
+                v[ii + NB * a] = val;
+            }
+        }
+    }
+    template <int R>
+    FCD_HD static void butterflies(cx<T>* v) {
+        constexpr int NB = 16 / R;
+        FCD_UNROLL
+        for (int ii = 0; ii < NB; ++ii) Dft<R, NB, DIR, T>::run(v + ii);
+    }
+    template <int R, int PP>
+    FCD_HD static void scatter(const cx<T>* v, int t, cx<T>* s) {
+        constexpr int NB = 16 / R;
+        FCD_UNROLL
+        for (int ii = 0; ii < NB; ++ii) {
+            const int i = t + TPF * ii;
+            const int k = i & (PP - 1);
+            const int j = (i - k) * R + k;
+            FCD_UNROLL
+            for (int a = 0; a < R; ++a) s[fft_pos(j + a * PP)] = v[ii + NB * a];
+        }
+    }
+
+    // ---- the four steps; a block-wide barrier is required between consecutive steps ----
+    // A: v (natural ownership)  -> pass-1 butterflies -> smem
+    FCD_HD static void stepA(cx<T>* v, int t, cx<T>* s) {
+        butterflies<R1>(v);
+        scatter<R1, 1>(v, t, s);
+    }
+    // B: smem -> v (twiddled)          [three-pass plans only]
+    FCD_HD static void stepB(cx<T>* v, int t, const cx<T>* s, const cx<T>* __restrict__ table) {
+        if constexpr (THREE) gather<R2, R1>(v, t, s, table);
+    }
+    // C: pass-2 butterflies -> smem    [three-pass plans only]
+    FCD_HD static void stepC(cx<T>* v, int t, cx<T>* s) {
+        if constexpr (THREE) {
+            butterflies<R2>(v);
+            scatter<R2, R1>(v, t, s);
+        }
+    }
+    // D: smem -> last-pass butterflies -> v (natural ownership)
+    FCD_HD static void stepD(cx<T>* v, int t, const cx<T>* s, const cx<T>* __restrict__ table) {
+        gather<R3, R1 * R2>(v, t, s, table);
+        butterflies<R3>(v);
+    }
+};
+
+}  // namespace fcd

@@ -1,0 +1,136 @@
+"""Mirror of the reference's ``pyfcd/fcd.py`` (class ``fcd``): same classmethods, argument
+order and return values, running on the B200 kernels.  ``fourier`` and ``Carrier`` are
+re-exported because callers import them from here (pyval/val.py:36)."""
+import numpy as np
+import torch
+
+from fcd_b200 import engine as _eng
+from pyfcd.fourier import fourier
+from pyfcd.carriers import Carrier
+
+
+class fcd:
+
+    @classmethod
+    def compute_height_map(cls, reference, displaced, square_size, layers=None, height=None, unwrap=True):
+        """Reference: pyfcd/fcd.py:14-35.  Returns (height_map float64 [N0,N1],
+        phases float64 [2,N0,N1], calibration_factor), caller-owned writable numpy arrays.
+        The arithmetic is the fused float32 CUDA pipeline (carrier detection and ccsgn in
+        float64); `phases` equal the reference's up to one global 2*pi*k per map."""
+        height = _eng.resolve_height(layers, height)
+        plan = _eng.get_plan(np.shape(reference), 1)
+        calibration_factor = plan.bind(reference, square_size=square_size, height=height)
+        frame = _eng.to_device_image(displaced, plan.device, allow_f64=False)
+        height_map, phases = plan.execute(frame, phases=True, unwrap=unwrap)
+        return (height_map.to(torch.float64).cpu().numpy(), phases.to(torch.float64).cpu().numpy(),
+                calibration_factor)
+
+    @classmethod
+    def height_from_layers(cls, layers):
+        """Reference: pyfcd/fcd.py:38-47."""
+        return _eng.height_from_layers(layers)
+
+    @classmethod
+    def effective_height(cls, layers, i):
+        """Reference: pyfcd/fcd.py:50-51 (index 2 hard-coded there)."""
+        return layers[2][1] * ((layers[i][0]) / (layers[i][1]))
+
+    @classmethod
+    def compute_carriers(cls, reference, square_size):
+        """Reference: pyfcd/fcd.py:54-70.  Returns ([Carrier, Carrier], calibration_factor)."""
+        calibration_factor, peaks = cls.compute_calibration_factor(square_size, reference)
+        peak_radius = np.linalg.norm(peaks[0] - peaks[1]) / 2
+        carriers = [Carrier(reference, calibration_factor, peak, peak_radius) for peak in peaks]
+        return carriers, calibration_factor
+
+    @classmethod
+    def compute_calibration_factor(cls, square_size, reference, plot=False):
+        """Reference: pyfcd/fcd.py:73-101 (note: square_size comes first)."""
+        peaks = fourier.find_peaks(reference)
+        pixel_frequencies = fourier.pixel_to_wavenumber(np.shape(reference), peaks)
+        pixel_wavelength = 2 * np.pi / np.mean(np.abs(pixel_frequencies))
+        physical_wavelength = 2 * square_size
+        if plot:
+            import matplotlib.pyplot as plt
+            fig, ax = plt.subplots()
+            ax.imshow(np.asarray(reference), cmap='gray')
+            ax.set_title(f"Calibration factor: \n {physical_wavelength / pixel_wavelength} dist/px")
+            n0, n1 = np.shape(reference)
+            ax.plot([n0 / 2, n0 / 2 + pixel_wavelength], [n1 / 2, n1 / 2], '.-', label=r'$\lambda$')
+            ax.set_xlabel("X (pix)")
+            ax.set_ylabel("Y (pix)")
+            plt.legend()
+            plt.tight_layout()
+            plt.show()
+        return physical_wavelength / pixel_wavelength, peaks
+
+    @classmethod
+    def compute_phases(cls, displaced_fft, carriers, unwrap=True):
+        """Reference: pyfcd/fcd.py:104-120, for a user-supplied spectrum and carriers (float64).
+        Inverse transforms run on the hand-written float64 FFT kernels; the unwrap follows the
+        same path as the fused kernel (rows from the centre column, rows linked along it)."""
+        dfft = np.asarray(displaced_fft)
+        plan = _eng.get_plan(dfft.shape)
+        dev = plan.device
+        f = torch.from_numpy(np.ascontiguousarray(dfft)).to(dev).to(torch.complex128)
+        phases = np.zeros((2, *dfft.shape))
+        for i, carrier in enumerate(carriers):
+            mask = torch.from_numpy(np.ascontiguousarray(carrier.mask)).to(dev)
+            cc = torch.from_numpy(np.ascontiguousarray(carrier.ccsgn)).to(dev).to(torch.complex128)
+            ang = -torch.angle(plan.fft2_c128(f * mask, inverse=True) * cc)
+            phases[i] = (_unwrap_scan(ang) if unwrap else ang).cpu().numpy()
+        return phases
+
+    @classmethod
+    def compute_displacement_field(cls, phases, carriers):
+        """Reference: pyfcd/fcd.py:123-138 (u along columns, v along rows)."""
+        _eng._require_cuda()
+        ph = torch.from_numpy(np.ascontiguousarray(np.asarray(phases, dtype=np.float64))).cuda()
+        f0, f1 = carriers[0].frequencies, carriers[1].frequencies
+        det_a = f0[1] * f1[0] - f0[0] * f1[1]
+        u = (f1[0] * ph[0] - f0[0] * ph[1]) / det_a
+        v = (f0[1] * ph[1] - f1[1] * ph[0]) / det_a
+        return torch.stack([u, v]).cpu().numpy()
+
+    @staticmethod
+    def fft_peaks(image):
+        """Plot of the log spectrum with candidate and chosen peaks.  Reference: pyfcd/fcd.py:142-176."""
+        import matplotlib.pyplot as plt
+        image = np.asarray(image)
+        plan = _eng.get_plan(image.shape)
+        img64 = torch.from_numpy(np.ascontiguousarray(image)).to(plan.device).to(torch.float64)
+        raw = torch.fft.fftshift(torch.abs(plan.fft2_c128((img64 - img64.mean()).to(torch.complex128))))
+        log_fft = torch.log1p(raw).cpu().numpy()
+        image_fft, mx = plan.highpass_spectrum(image)
+        peak_locations = plan.peak_locations(image_fft, 0.5 * mx, 4)
+        rightmost_peak, perpendicular_peak = fourier.find_peaks(image)
+        fig, ax = plt.subplots()
+        ax.imshow(log_fft, origin='lower', cmap='magma')
+        ax.set_title("FFT Spectrum with Peaks")
+        ax.set_xlabel(r"$k_x$ (1/pix)")
+        ax.set_ylabel(r"$k_y$ (1/pix)")
+        for i, (y, x) in enumerate(peak_locations):
+            ax.plot(x, y, 'k.', markersize=6)
+            ax.text(x + 5, y + 5, f"peak {i+1}", color='white', fontsize=9)
+        ax.plot(rightmost_peak[1], rightmost_peak[0], 'r.', label='Rightmost peak')
+        ax.plot(perpendicular_peak[1], perpendicular_peak[0], 'b.', label=r'$\perp$ peak')
+        ax.legend()
+        plt.tight_layout()
+        plt.show()
+
+
+def _unwrap_scan(w: torch.Tensor) -> torch.Tensor:
+    """Row/column path unwrap on the device, anchored at the centre pixel (same path as the
+    fused kernels: RowDemod + RowLink in csrc/fcd_kernels.cuh)."""
+    two_pi = 2.0 * np.pi
+    n0, n1 = w.shape
+    jr = torch.zeros_like(w, dtype=torch.int64)
+    jr[:, 1:] = torch.round((w[:, 1:] - w[:, :-1]) / two_pi).to(torch.int64)
+    c = torch.cumsum(jr, dim=1)
+    c = c - c[:, n1 // 2:n1 // 2 + 1]
+    col = w[:, n1 // 2]
+    jc = torch.zeros(n0, dtype=torch.int64, device=w.device)
+    jc[1:] = torch.round((col[1:] - col[:-1]) / two_pi).to(torch.int64)
+    m = torch.cumsum(jc, dim=0)
+    m = m - m[n0 // 2]
+    return w - two_pi * (c + m[:, None]).to(w.dtype)
