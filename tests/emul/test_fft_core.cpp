@@ -9,11 +9,7 @@ using namespace fcd;
 
 template <int L, int DIR, class T> double run_one() {
     using F = Fft<L, DIR, T>;
-    std::vector<cx<T>> table(L);
-    for (int n = 0; n < L; ++n) {
-        long double a = -2.0L * M_PIl * n / L;
-        table[n] = mk<T>((T)cosl(a), (T)sinl(a));
-    }
+    std::vector<cx<T>> table = F::make_table();
     std::vector<std::complex<long double>> x(L), ref(L);
     unsigned s = 12345u + L;
     for (int n = 0; n < L; ++n) {

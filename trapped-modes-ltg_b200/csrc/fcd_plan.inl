@@ -90,25 +90,19 @@ struct PlanImpl {
     rt::StageTimer timer;
 
     // ------------------------------------------------------------------ construction ----
-    template <class T>
-    static std::vector<cx<T>> make_twiddles(int n) {
-        std::vector<cx<T>> t(n);
-        for (int j = 0; j < n; ++j) {
-            const long double a = -2.0L * 3.14159265358979323846264338327950288L * j / n;
-            t[j] = mk<T>((T)cosl(a), (T)sinl(a));
-        }
-        return t;
-    }
-
     void init(int rows, int cols, int frames_per_launch) {
         if (!supported_dim(rows) || !supported_dim(cols))
             rt::fail("unsupported shape: rows and cols must be powers of two in [64, 4096]");
         if (frames_per_launch < 1 || frames_per_launch > 16384) rt::fail("frames_per_launch out of range");
         H = rows; W = cols; chunk = frames_per_launch;
-        tw_w_f.upload(make_twiddles<float>(W), nullptr);
-        tw_h_f.upload(make_twiddles<float>(H), nullptr);
-        tw_w_d.upload(make_twiddles<double>(W), nullptr);
-        tw_h_d.upload(make_twiddles<double>(H), nullptr);
+        FCD_DISPATCH_L(W, {
+            tw_w_f.upload(Fft<L, -1, float>::make_table(), nullptr);
+            tw_w_d.upload(Fft<L, -1, double>::make_table(), nullptr);
+        })
+        FCD_DISPATCH_L(H, {
+            tw_h_f.upload(Fft<L, -1, float>::make_table(), nullptr);
+            tw_h_d.upload(Fft<L, -1, double>::make_table(), nullptr);
+        })
         w4p = W / 2 + 4;
     }
 

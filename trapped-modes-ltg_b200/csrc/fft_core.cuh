@@ -18,7 +18,9 @@
 // The code is __host__ __device__ so that tests/emul can execute exactly the same
 // arithmetic and index maps on the CPU (this container has no GPU).
 #pragma once
+#include <cmath>
 #include <cstdint>
+#include <vector>
 
 #if defined(__CUDACC__)
 #define FCD_HD __host__ __device__ __forceinline__
@@ -157,10 +159,27 @@ struct Fft {
     static constexpr int SMEM = L + L / 16;    // elements of the padded exchange buffer
     static constexpr bool THREE = (R2 != 1);
 
-    // twiddle W_L^n (table holds exp(-2 pi i n / L)); DIR=+1 conjugates
-    FCD_HD static cx<T> tw(const cx<T>* __restrict__ table, int n) {
-        cx<T> w = table[n];
-        return DIR < 0 ? w : conj(w);
+    // Twiddle table, laid out per pass as [a][k] so that consecutive threads (consecutive k)
+    // read consecutive elements:  pass with radix R after prior product PP needs
+    // W_{PP*R}^{k*a}, k in [0,PP), a in [1,R)  ->  table[off + a*PP + k].
+    // Block of the middle pass (three-pass plans) first, then the block of the last pass.
+    static constexpr int TW_MID = THREE ? R1 * R2 : 0;
+    static constexpr int TW_ELEMS = TW_MID + L;
+    template <int R, int PP> static constexpr int tw_off() { return (THREE && PP == R1) ? 0 : TW_MID; }
+
+    // host: build the table (forward sign; DIR=+1 conjugates on load)
+    static std::vector<cx<T>> make_table() {
+        std::vector<cx<T>> t((size_t)TW_ELEMS);
+        auto fill = [&](int off, int R, int PP) {
+            for (int a = 0; a < R; ++a)
+                for (int k = 0; k < PP; ++k) {
+                    const long double ang = -2.0L * 3.14159265358979323846264338327950288L * ((long long)k * a) / (PP * R);
+                    t[(size_t)off + (size_t)a * PP + k] = mk<T>((T)cosl(ang), (T)sinl(ang));
+                }
+        };
+        if (THREE) fill(0, R2, R1);
+        fill(TW_MID, R3, R1 * R2);
+        return t;
     }
 
     // gather butterfly inputs of a pass with radix R and prior product PP; apply twiddles
@@ -171,10 +190,14 @@ struct Fft {
         for (int ii = 0; ii < NB; ++ii) {
             const int i = t + TPF * ii;
             const int k = i & (PP - 1);
+            const cx<T>* __restrict__ tw = table + tw_off<R, PP>() + k;
             FCD_UNROLL
             for (int a = 0; a < R; ++a) {
                 cx<T> val = s[fft_pos(i + a * (L / R))];
-                if (PP > 1 && a > 0) val = val * tw(table, (L / (PP * R)) * k * a);
+                if (PP > 1 && a > 0) {
+                    const cx<T> w = tw[a * PP];
+                    val = val * (DIR < 0 ? w : conj(w));
+                }
                 v[ii + NB * a] = val;
             }
         }
