@@ -49,7 +49,7 @@ struct GenRowsParams {
 };
 
 template <int L, int G, int DIR, class T>
-struct GenRows {
+struct GenRows : NoPrologue {
     using F = Fft<L, DIR, T>;
     using Params = GenRowsParams<T>;
     static constexpr int TPF = L / 16, THREADS = G * TPF, PHASES = 4;
@@ -101,7 +101,7 @@ struct GenColsParams {
 };
 
 template <int L, int G, int DIR, class T>
-struct GenCols {
+struct GenCols : NoPrologue {
     using F = Fft<L, DIR, T>;
     using Params = GenColsParams<T>;
     static constexpr int TPF = L / 16, THREADS = G * TPF, PHASES = 4;
@@ -142,7 +142,7 @@ struct SumParams {
     double* out;   // single accumulator, zero-initialised
     int nblocks;
 };
-struct SumKernel {
+struct SumKernel : NoPrologue {
     using Params = SumParams;
     static constexpr int THREADS = 256, PHASES = 2, SMEM_BYTES = THREADS * (int)sizeof(double);
     struct State { int dummy; };
@@ -176,7 +176,7 @@ struct SpecMagParams {
     unsigned long long* maxbits;
     int H, W, nblocks;
 };
-struct SpecMag {
+struct SpecMag : NoPrologue {
     using Params = SpecMagParams;
     static constexpr int THREADS = 256, PHASES = 1, SMEM_BYTES = 16;
     struct State { int dummy; };
@@ -207,7 +207,7 @@ struct CandidatesParams {
     int capacity;
     int H, W, nblocks;
 };
-struct Candidates {
+struct Candidates : NoPrologue {
     using Params = CandidatesParams;
     static constexpr int THREADS = 256, PHASES = 1, SMEM_BYTES = 16;
     struct State { int dummy; };
@@ -236,7 +236,7 @@ struct MaskMulParams {
     int H, W, nblocks;
     uint8_t* mask_out;     // optional [H][W] unshifted boolean mask (Carrier.mask)
 };
-struct MaskMul {
+struct MaskMul : NoPrologue {
     using Params = MaskMulParams;
     static constexpr int THREADS = 256, PHASES = 1, SMEM_BYTES = 16;
     struct State { int dummy; };
@@ -263,7 +263,7 @@ struct CcsgnStoreParams {
     long long n;
     int nblocks;
 };
-struct CcsgnStore {
+struct CcsgnStore : NoPrologue {
     using Params = CcsgnStoreParams;
     static constexpr int THREADS = 256, PHASES = 1, SMEM_BYTES = 16;
     struct State { int dummy; };

@@ -28,6 +28,39 @@ constexpr float kInvTwoPiF = 0.15915494309189533577f;
 
 FCD_HD int imin(int a, int b) { return a < b ? a : b; }
 
+FCD_HD float fast_div(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fdividef(a, b);
+#else
+    return a / b;
+#endif
+}
+
+// Branch-free atan2 (max abs error 3e-7 rad, i.e. about one ulp of pi in float32).  The
+// library atan2f compiles to calls and divergent slow paths, which stops the compiler from
+// batching the loads around it (ncu profiles/r01: one exposed DRAM round trip per element).
+// np.angle(0) = 0 is preserved.
+FCD_HD float fast_atan2f(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float a = fast_div(mn, mx);
+    const float s = a * a;
+    float r = 0.002456723479554057f;
+    r = r * s + -0.01440135296434164f;
+    r = r * s + 0.03978121653199196f;
+    r = r * s + -0.07234856486320496f;
+    r = r * s + 0.10498945415019989f;
+    r = r * s + -0.14161229133605957f;
+    r = r * s + 0.19985906779766083f;
+    r = r * s + -0.33332598209381104f;
+    r = r * s + 0.9999998807907104f;
+    r = r * a;
+    r = (ay > ax) ? 1.57079632679489661923f - r : r;
+    r = (x < 0.f) ? 3.14159265358979323846f - r : r;
+    r = (mx > 0.f) ? r : 0.f;
+    return copysignf(r, y);
+}
+
 // common helpers -------------------------------------------------------------------------
 template <int L, int G>
 struct GroupLayout {
@@ -40,6 +73,21 @@ struct GroupLayout {
 
 struct alignas(16) cf2 {
     cf a, b;
+};
+
+// Blocks are persistent: they copy the twiddle table of their transform length into shared
+// memory once (prologue) and then loop over tiles, so twiddle reads are LDS, not LDG.
+template <class F, int THREADS>
+struct SmemTwiddles {
+    static constexpr int TW_BYTES = F::TW_ELEMS * (int)sizeof(cf);
+    static_assert(TW_BYTES % 16 == 0, "twiddle block must keep 16-byte alignment");
+    FCD_HD static void load(const cf* __restrict__ g, int tid, unsigned char* smem) {
+        cf* s = reinterpret_cast<cf*>(smem);
+        for (int i = tid; i < F::TW_ELEMS; i += THREADS) s[i] = g[i];
+    }
+};
+struct NoPrologue {
+    template <class P> FCD_HD static void prologue(const P&, int, unsigned char*) {}
 };
 
 // =========================================================================================
@@ -64,11 +112,15 @@ struct RowFwd {
     using GL = GroupLayout<L, G>;
     using Params = RowFwdParams;
     static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 6;
-    static constexpr int SMEM_BYTES = G * GL::STRIDE * (int)sizeof(cf);
+    using TW = SmemTwiddles<F, THREADS>;
+    static constexpr int SMEM_BYTES = TW::TW_BYTES + G * GL::STRIDE * (int)sizeof(cf);
+    FCD_HD static void prologue(const Params& p, int tid, unsigned char* smem) { TW::load(p.tw, tid, smem); }
     struct State { cf v[16]; };
 
     template <int PH>
-    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem, State& st) {
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem_all, State& st) {
+        const cf* tw = reinterpret_cast<const cf*>(smem_all);
+        unsigned char* smem = smem_all + TW::TW_BYTES;
         const int g = tid / TPF, t = tid % TPF;
         cf* s = reinterpret_cast<cf*>(smem) + g * GL::STRIDE;
         const int W = L;
@@ -96,11 +148,11 @@ struct RowFwd {
             }
             F::stepA(st.v, t, s);
         } else if constexpr (PH == 1) {
-            F::stepB(st.v, t, s, p.tw);
+            F::stepB(st.v, t, s, tw);
         } else if constexpr (PH == 2) {
             F::stepC(st.v, t, s);
         } else if constexpr (PH == 3) {
-            F::stepD(st.v, t, s, p.tw);
+            F::stepD(st.v, t, s, tw);
         } else if constexpr (PH == 4) {
             FCD_UNROLL
             for (int m = 0; m < 16; ++m) s[fft_pos(t + TPF * m)] = st.v[m];
@@ -148,11 +200,15 @@ struct ColBand {
     using GL = GroupLayout<L, G>;
     using Params = ColBandParams;
     static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 10;
-    static constexpr int SMEM_BYTES = G * GL::STRIDE * (int)sizeof(cf);
+    using TW = SmemTwiddles<FF, THREADS>;
+    static constexpr int SMEM_BYTES = TW::TW_BYTES + G * GL::STRIDE * (int)sizeof(cf);
+    FCD_HD static void prologue(const Params& p, int tid, unsigned char* smem) { TW::load(p.tw, tid, smem); }
     struct State { cf v[16]; };
 
     template <int PH>
-    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem, State& st) {
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem_all, State& st) {
+        const cf* tw = reinterpret_cast<const cf*>(smem_all);
+        unsigned char* smem = smem_all + TW::TW_BYTES;
         const int g = tid / TPF, t = tid % TPF;
         cf* s = reinterpret_cast<cf*>(smem) + g * GL::STRIDE;
         const int H = L;
@@ -169,11 +225,11 @@ struct ColBand {
             }
             FF::stepA(st.v, t, s);
         } else if constexpr (PH == 1) {
-            FF::stepB(st.v, t, s, p.tw);
+            FF::stepB(st.v, t, s, tw);
         } else if constexpr (PH == 2) {
             FF::stepC(st.v, t, s);
         } else if constexpr (PH == 3) {
-            FF::stepD(st.v, t, s, p.tw);
+            FF::stepD(st.v, t, s, tw);
             int lo = 1, hi = 0;
             if (c < p.nc[i]) { lo = p.chord_lo[i * p.ncp + c]; hi = p.chord_hi[i * p.ncp + c]; }
             FCD_UNROLL
@@ -185,11 +241,11 @@ struct ColBand {
         } else if constexpr (PH == 4) {
             FI::stepA(st.v, t, s);
         } else if constexpr (PH == 5) {
-            FI::stepB(st.v, t, s, p.tw);
+            FI::stepB(st.v, t, s, tw);
         } else if constexpr (PH == 6) {
             FI::stepC(st.v, t, s);
         } else if constexpr (PH == 7) {
-            FI::stepD(st.v, t, s, p.tw);
+            FI::stepD(st.v, t, s, tw);
         } else if constexpr (PH == 8) {
             FCD_UNROLL
             for (int m = 0; m < 16; ++m) s[fft_pos(t + TPF * m)] = st.v[m];
@@ -237,7 +293,9 @@ struct RowDemod {
     // per group: exchange buffer (aliased by the jump scan), chunk totals, chunk offsets, flag
     static constexpr int AUX_INTS = 4 * TPF + 4;
     static constexpr int GROUP_BYTES = GL::STRIDE * (int)sizeof(cf) + AUX_INTS * (int)sizeof(int);
-    static constexpr int SMEM_BYTES = G * GROUP_BYTES;
+    using TW = SmemTwiddles<FF, THREADS>;
+    static constexpr int SMEM_BYTES = TW::TW_BYTES + G * GROUP_BYTES;
+    FCD_HD static void prologue(const Params& p, int tid, unsigned char* smem) { TW::load(p.tw, tid, smem); }
     struct State {
         cf v[16];
         float ph0[16], ph1[16];
@@ -256,16 +314,21 @@ struct RowDemod {
     }
     FCD_HD static void demod(const Params& p, int i, int y, int t, const cf* v, float* ph) {
         const int W = L;
-        const cf* cc = p.ccsgn + ((long long)i * p.H + y) * W;
+        const cf* __restrict__ cc = p.ccsgn + ((long long)i * p.H + y) * W;
+        cf c[16];
+        FCD_UNROLL
+        for (int m = 0; m < 16; ++m) c[m] = cc[t + TPF * m];     // all loads in flight first
         FCD_UNROLL
         for (int m = 0; m < 16; ++m) {
-            const cf q = v[m] * cc[t + TPF * m];
-            ph[m] = -atan2f(q.y, q.x);
+            const cf q = v[m] * c[m];
+            ph[m] = -fast_atan2f(q.y, q.x);
         }
     }
 
     template <int PH>
-    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem, State& st) {
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem_all, State& st) {
+        const cf* tw = reinterpret_cast<const cf*>(smem_all);
+        unsigned char* smem = smem_all + TW::TW_BYTES;
         const int g = tid / TPF, t = tid % TPF;
         unsigned char* gbase = smem + (size_t)g * GROUP_BYTES;
         cf* s = reinterpret_cast<cf*>(gbase);
@@ -275,28 +338,28 @@ struct RowDemod {
         int2s* off = reinterpret_cast<int2s*>(aux + 2 * TPF);   // [TPF]
         int* flag = aux + 4 * TPF;
         const int W = L;
-        const int y = bx * G + g;
-        const int f = by;
+        const int y = by * G + g;   // tiles are ordered frame-fastest so that consecutive tiles of
+        const int f = bx;           // a block reuse the same ccsgn rows out of L2
         if constexpr (PH == 0) {
             if (t == 0) *flag = 0;
             load_band(p, f, 0, y, t, st.v);
             FI::stepA(st.v, t, s);
         } else if constexpr (PH == 1) {
-            FI::stepB(st.v, t, s, p.tw);
+            FI::stepB(st.v, t, s, tw);
         } else if constexpr (PH == 2) {
             FI::stepC(st.v, t, s);
         } else if constexpr (PH == 3) {
-            FI::stepD(st.v, t, s, p.tw);
+            FI::stepD(st.v, t, s, tw);
             demod(p, 0, y, t, st.v, st.ph0);
         } else if constexpr (PH == 4) {
             load_band(p, f, 1, y, t, st.v);
             FI::stepA(st.v, t, s);
         } else if constexpr (PH == 5) {
-            FI::stepB(st.v, t, s, p.tw);
+            FI::stepB(st.v, t, s, tw);
         } else if constexpr (PH == 6) {
             FI::stepC(st.v, t, s);
         } else if constexpr (PH == 7) {
-            FI::stepD(st.v, t, s, p.tw);
+            FI::stepD(st.v, t, s, tw);
             demod(p, 1, y, t, st.v, st.ph1);
             // wrapped phase at the anchor column links the rows (K3b)
             if (t == (p.x_ref % TPF)) {
@@ -388,11 +451,11 @@ struct RowDemod {
         } else if constexpr (PH == 14) {
             FF::stepA(st.v, t, s);
         } else if constexpr (PH == 15) {
-            FF::stepB(st.v, t, s, p.tw);
+            FF::stepB(st.v, t, s, tw);
         } else if constexpr (PH == 16) {
             FF::stepC(st.v, t, s);
         } else {
-            FF::stepD(st.v, t, s, p.tw);
+            FF::stepD(st.v, t, s, tw);
             cf* o = p.w3 + ((long long)f * p.H + y) * W;
             FCD_UNROLL
             for (int m = 0; m < 16; ++m) o[t + TPF * m] = st.v[m];
@@ -411,7 +474,7 @@ struct RowLinkParams {
     int unwrap;
 };
 
-struct RowLink {
+struct RowLink : NoPrologue {
     using Params = RowLinkParams;
     static constexpr int THREADS = 256, PHASES = 4;
     static constexpr int MAXH = 4096;
@@ -460,7 +523,7 @@ struct PhaseFixParams {
     const float* rowoff;   // [F][2][H]
     int H, W;
 };
-struct PhaseFix {
+struct PhaseFix : NoPrologue {
     using Params = PhaseFixParams;
     static constexpr int THREADS = 256, PHASES = 1, SMEM_BYTES = 16;
     struct State { int dummy; };
@@ -488,8 +551,7 @@ struct ColIntegrateParams {
     const cf* tw;
     const float* kx;       // [W]  column wavenumbers (plain, used for k^2)
     const float* kxq;      // [W]  with index W/2+1 zeroed (fourier.py:89)
-    const float* ky;       // [H]
-    const float* kyq;      // [H]  with index H/2+1 zeroed (fourier.py:92)
+    float dky;             // row wavenumber step: ky[kr] = signed(kr) * dky; index H/2+1 zeroed (fourier.py:92)
     int W, w4p;
     float f0r, f0c, f1r, f1c;   // carrier wavevectors [k_row, k_col] (fcd.py:134-137)
     float scale;                // 1 / (2 * height * det * H * W)
@@ -503,7 +565,9 @@ struct ColIntegrate {
     using GL = GroupLayout<L, G>;
     using Params = ColIntegrateParams;
     static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 16;
-    static constexpr int SMEM_BYTES = G * GL::STRIDE * (int)sizeof(cf);
+    using TW = SmemTwiddles<FF, THREADS>;
+    static constexpr int SMEM_BYTES = TW::TW_BYTES + G * GL::STRIDE * (int)sizeof(cf);
+    FCD_HD static void prologue(const Params& p, int tid, unsigned char* smem) { TW::load(p.tw, tid, smem); }
     struct State { cf v[16]; cf va[16]; };
 
     FCD_HD static void load_col(const Params& p, int f, int kc, int t, cf* v) {
@@ -524,7 +588,9 @@ struct ColIntegrate {
     }
 
     template <int PH>
-    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem, State& st) {
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem_all, State& st) {
+        const cf* tw = reinterpret_cast<const cf*>(smem_all);
+        unsigned char* smem = smem_all + TW::TW_BYTES;
         const int g = tid / TPF, t = tid % TPF;
         cf* s = reinterpret_cast<cf*>(smem) + g * GL::STRIDE;
         const int H = L;
@@ -537,11 +603,11 @@ struct ColIntegrate {
             else { FCD_UNROLL for (int m = 0; m < 16; ++m) st.v[m] = mk<float>(0.f, 0.f); }
             FF::stepA(st.v, t, s);
         } else if constexpr (PH == 1) {
-            FF::stepB(st.v, t, s, p.tw);
+            FF::stepB(st.v, t, s, tw);
         } else if constexpr (PH == 2) {
             FF::stepC(st.v, t, s);
         } else if constexpr (PH == 3) {
-            FF::stepD(st.v, t, s, p.tw);
+            FF::stepD(st.v, t, s, tw);
             FCD_UNROLL
             for (int m = 0; m < 16; ++m) st.va[m] = st.v[m];
         } else if constexpr (PH == 4) {
@@ -549,11 +615,11 @@ struct ColIntegrate {
             else { FCD_UNROLL for (int m = 0; m < 16; ++m) st.v[m] = mk<float>(0.f, 0.f); }
             FF::stepA(st.v, t, s);
         } else if constexpr (PH == 5) {
-            FF::stepB(st.v, t, s, p.tw);
+            FF::stepB(st.v, t, s, tw);
         } else if constexpr (PH == 6) {
             FF::stepC(st.v, t, s);
         } else if constexpr (PH == 7) {
-            FF::stepD(st.v, t, s, p.tw);
+            FF::stepD(st.v, t, s, tw);
         } else if constexpr (PH == 8) {
             FCD_UNROLL
             for (int m = 0; m < 16; ++m) s[fft_pos(t + TPF * m)] = st.v[m];
@@ -568,10 +634,13 @@ struct ColIntegrate {
                     const cf z = st.va[m];                      // Z(kr, kc)
                     const cf p0 = z + zm;                       // 2 * Phi0(k)
                     const cf p1 = mul_mi(z - zm);               // 2 * Phi1(k)
-                    const float kyv = p.ky[kr], kya = p.kyq[kr], kyb = p.kyq[krm];
+                    const float kyv = (float)(kr < H / 2 ? kr : kr - H) * p.dky;          // ky[kr]
+                    const float kya = (kr == H / 2 + 1) ? 0.f : kyv;                     // quirk-zeroed ky[kr]
+                    const float kym = (kr == H / 2) ? kyv : -kyv;                        // ky[-kr]
+                    const float kyb = (kr == H / 2 - 1) ? 0.f : kym;                     // quirk-zeroed ky[-kr]
                     float k2 = kxv * kxv + kyv * kyv;
                     if (kr == 0 && kc == 0) k2 = 1.f;
-                    const float ik2 = 1.0f / k2;
+                    const float ik2 = fast_div(1.0f, k2);
                     // a(k), a(-k) and b(k), b(-k): coefficients of Phi0, Phi1 in hhat / i
                     const float a_p = kxa * p.f1r - kya * p.f1c, a_m = kxb * p.f1r - kyb * p.f1c;
                     const float b_p = kya * p.f0c - kxa * p.f0r, b_m = kyb * p.f0c - kxb * p.f0r;
@@ -587,11 +656,11 @@ struct ColIntegrate {
         } else if constexpr (PH == 10) {
             FI::stepA(st.v, t, s);
         } else if constexpr (PH == 11) {
-            FI::stepB(st.v, t, s, p.tw);
+            FI::stepB(st.v, t, s, tw);
         } else if constexpr (PH == 12) {
             FI::stepC(st.v, t, s);
         } else if constexpr (PH == 13) {
-            FI::stepD(st.v, t, s, p.tw);
+            FI::stepD(st.v, t, s, tw);
         } else if constexpr (PH == 14) {
             FCD_UNROLL
             for (int m = 0; m < 16; ++m) s[fft_pos(t + TPF * m)] = st.v[m];
@@ -624,11 +693,15 @@ struct RowInv {
     using GL = GroupLayout<L, G>;
     using Params = RowInvParams;
     static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 4;
-    static constexpr int SMEM_BYTES = G * GL::STRIDE * (int)sizeof(cf);
+    using TW = SmemTwiddles<FI, THREADS>;
+    static constexpr int SMEM_BYTES = TW::TW_BYTES + G * GL::STRIDE * (int)sizeof(cf);
+    FCD_HD static void prologue(const Params& p, int tid, unsigned char* smem) { TW::load(p.tw, tid, smem); }
     struct State { cf v[16]; };
 
     template <int PH>
-    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem, State& st) {
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem_all, State& st) {
+        const cf* tw = reinterpret_cast<const cf*>(smem_all);
+        unsigned char* smem = smem_all + TW::TW_BYTES;
         const int g = tid / TPF, t = tid % TPF;
         cf* s = reinterpret_cast<cf*>(smem) + g * GL::STRIDE;
         const int W = L;
@@ -648,11 +721,11 @@ struct RowInv {
             }
             FI::stepA(st.v, t, s);
         } else if constexpr (PH == 1) {
-            FI::stepB(st.v, t, s, p.tw);
+            FI::stepB(st.v, t, s, tw);
         } else if constexpr (PH == 2) {
             FI::stepC(st.v, t, s);
         } else {
-            FI::stepD(st.v, t, s, p.tw);
+            FI::stepD(st.v, t, s, tw);
             float* oa = p.height + ((long long)by * p.H + ya) * W;
             float* ob = oa + W;
             if (p.mask) {

@@ -45,10 +45,16 @@ inline void emu_phases(const typename K::Params& p, int bx, int by, unsigned cha
 
 template <class K>
 inline void launch(int gx, int gy, stream_t, const typename K::Params& p) {
-    std::vector<unsigned char> smem((size_t)K::SMEM_BYTES + 16);
-    std::vector<typename K::State> st(K::THREADS);
-    for (int by = 0; by < gy; ++by)
-        for (int bx = 0; bx < gx; ++bx) emu_phases<K, 0>(p, bx, by, smem.data(), st.data());
+    // persistent blocks: a few emulated blocks loop over all tiles, like the device does
+    const int ntiles = gx * gy;
+    const int grid = ntiles < 3 ? ntiles : 3;
+    for (int b = 0; b < grid; ++b) {
+        std::vector<unsigned char> smem((size_t)K::SMEM_BYTES + 16, 0xCD);
+        std::vector<typename K::State> st(K::THREADS);
+        for (int tid = 0; tid < K::THREADS; ++tid) K::prologue(p, tid, smem.data());
+        const int t0 = (int)((long long)b * ntiles / grid), t1 = (int)((long long)(b + 1) * ntiles / grid);
+        for (int tile = t0; tile < t1; ++tile) emu_phases<K, 0>(p, tile % gx, tile / gx, smem.data(), st.data());
+    }
 }
 
 #else
@@ -77,31 +83,51 @@ inline void d2d(void* d, const void* s_, size_t n, stream_t s) {
 inline void sync(stream_t s) { check(cudaStreamSynchronize((cudaStream_t)s), "cudaStreamSynchronize"); }
 
 template <class K, int PH>
-__device__ __forceinline__ void run_phases(const typename K::Params& p, unsigned char* smem, typename K::State& st) {
-    K::template phase<PH>(p, (int)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x, smem, st);
+__device__ __forceinline__ void run_phases(const typename K::Params& p, int bx, int by, unsigned char* smem,
+                                           typename K::State& st) {
+    K::template phase<PH>(p, bx, by, (int)threadIdx.x, smem, st);
     if constexpr (PH + 1 < K::PHASES) {
         __syncthreads();
-        run_phases<K, PH + 1>(p, smem, st);
+        run_phases<K, PH + 1>(p, bx, by, smem, st);
     }
 }
 
+// Persistent blocks: grid = min(tiles, SMs * resident blocks per SM); each block runs the
+// prologue once (twiddle table -> shared memory) and then loops over tiles (bx, by).
 template <class K>
-__global__ void __launch_bounds__(K::THREADS) fcd_kernel(const __grid_constant__ typename K::Params p) {
+__global__ void __launch_bounds__(K::THREADS) fcd_kernel(const __grid_constant__ typename K::Params p, int gx, int ntiles) {
     extern __shared__ __align__(16) unsigned char fcd_smem[];
     typename K::State st;
-    run_phases<K, 0>(p, fcd_smem, st);
+    K::prologue(p, (int)threadIdx.x, fcd_smem);
+    __syncthreads();
+    // contiguous tile range per block (bx fastest): neighbouring tiles share inputs in L2
+    const int t0 = (int)((long long)blockIdx.x * ntiles / gridDim.x);
+    const int t1 = (int)((long long)(blockIdx.x + 1) * ntiles / gridDim.x);
+    for (int tile = t0; tile < t1; ++tile) {
+        run_phases<K, 0>(p, tile % gx, tile / gx, fcd_smem, st);
+        __syncthreads();
+    }
 }
 
 template <class K>
 inline void launch(int gx, int gy, stream_t s, const typename K::Params& p) {
-    static bool configured = false;   // per kernel instantiation
-    if (!configured) {
+    static int resident = 0;   // per kernel instantiation: blocks that fit on the whole device
+    if (!resident) {
         if (K::SMEM_BYTES > 48 * 1024)
             check(cudaFuncSetAttribute(fcd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES),
                   "cudaFuncSetAttribute(smem)");
-        configured = true;
+        int dev = 0, sms = 0, per_sm = 0;
+        check(cudaGetDevice(&dev), "cudaGetDevice");
+        check(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute");
+        check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fcd_kernel<K>, K::THREADS, K::SMEM_BYTES),
+              "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+        if (per_sm < 1) fail("kernel does not fit on an SM");
+        resident = sms * per_sm;
     }
-    fcd_kernel<K><<<dim3((unsigned)gx, (unsigned)gy, 1), K::THREADS, K::SMEM_BYTES, (cudaStream_t)s>>>(p);
+    const int ntiles = gx * gy;
+    if (ntiles <= 0) return;
+    const int grid = ntiles < resident ? ntiles : resident;
+    fcd_kernel<K><<<dim3((unsigned)grid, 1, 1), K::THREADS, K::SMEM_BYTES, (cudaStream_t)s>>>(p, gx, ntiles);
     check(cudaGetLastError(), "kernel launch");
 }
 #endif

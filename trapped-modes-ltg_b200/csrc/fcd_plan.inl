@@ -69,7 +69,8 @@ struct PlanImpl {
     std::vector<int> h_lo, h_hi;           // [2][ncp]
     rt::DevBuf<int> chord_lo, chord_hi;
     rt::DevBuf<cf> ccsgn;                  // [2][H][W]
-    rt::DevBuf<float> kx, kxq, ky, kyq;
+    rt::DevBuf<float> kx, kxq;
+    float dky = 0.f;
     double f[2][2] = {{0, 0}, {0, 0}};     // carrier wavevectors [k_row, k_col]
     double det = 1;
 
@@ -328,12 +329,11 @@ struct PlanImpl {
         det = f[0][1] * f[1][0] - f[0][0] * f[1][1];                 // fcd.py:134-135
 
         // wavenumber vectors of integrate_in_fourier with the N//2+1 quirk (fourier.py:128-132)
-        std::vector<float> vkx(W), vkxq(W), vky(H), vkyq(H);
+        std::vector<float> vkx(W), vkxq(W);
         for (int j = 0; j < W; ++j) { vkx[j] = (float)fftfreq_at(W, d, j); vkxq[j] = vkx[j]; }
-        for (int j = 0; j < H; ++j) { vky[j] = (float)fftfreq_at(H, d, j); vkyq[j] = vky[j]; }
         vkxq[W / 2 + 1] = 0.f;
-        vkyq[H / 2 + 1] = 0.f;
-        kx.upload(vkx, s); kxq.upload(vkxq, s); ky.upload(vky, s); kyq.upload(vkyq, s);
+        kx.upload(vkx, s); kxq.upload(vkxq, s);
+        dky = (float)fftfreq_at(H, d, 1);
 
         // ccsgn_i = conj(ifft2(fft2(ref) * mask_i))   (carriers.py:22-24), float64 then stored c64
         fft2_d(ref, is_f64 ? 2 : 1, 0.0, spec.ptr, -1, s);
@@ -391,7 +391,7 @@ struct PlanImpl {
                 constexpr int G = Tune<L>::GDEM;
                 RowDemodParams p{w2.ptr, ccsgn.ptr, w3.ptr, colphase.ptr, po, tw_w_f.ptr, H, ncp,
                                  {nc[0], nc[1]}, {c_lo[0] - W / 2, c_lo[1] - W / 2}, W / 2, unwrap ? 1 : 0};
-                launch<RowDemod<L, G>>(H / G, nf, s, p);
+                launch<RowDemod<L, G>>(nf, H / G, s, p);
             })
             if (profiling) timer.mark(s, 2);
             launch<RowLink>(2, nf, s, RowLinkParams{colphase.ptr, rowoff.ptr, H, H / 2, unwrap ? 1 : 0});
@@ -402,7 +402,7 @@ struct PlanImpl {
             }
             FCD_DISPATCH_L(H, {
                 constexpr int G = Tune<L>::GCOL;
-                ColIntegrateParams p{w3.ptr, rowoff.ptr, w4.ptr, tw_h_f.ptr, kx.ptr, kxq.ptr, ky.ptr, kyq.ptr, W, w4p,
+                ColIntegrateParams p{w3.ptr, rowoff.ptr, w4.ptr, tw_h_f.ptr, kx.ptr, kxq.ptr, dky, W, w4p,
                                      (float)f[0][0], (float)f[0][1], (float)f[1][0], (float)f[1][1], scale_int,
                                      unwrap ? 1 : 0};
                 launch<ColIntegrate<L, G>>(ceil_div(W / 2 + 1, G), nf, s, p);

@@ -165,7 +165,6 @@ struct Fft {
     // Block of the middle pass (three-pass plans) first, then the block of the last pass.
     static constexpr int TW_MID = THREE ? R1 * R2 : 0;
     static constexpr int TW_ELEMS = TW_MID + L;
-    template <int R, int PP> static constexpr int tw_off() { return (THREE && PP == R1) ? 0 : TW_MID; }
 
     // host: build the table (forward sign; DIR=+1 conjugates on load)
     static std::vector<cx<T>> make_table() {
@@ -190,7 +189,8 @@ struct Fft {
         for (int ii = 0; ii < NB; ++ii) {
             const int i = t + TPF * ii;
             const int k = i & (PP - 1);
-            const cx<T>* __restrict__ tw = table + tw_off<R, PP>() + k;
+            constexpr int OFF = (THREE && PP == R1) ? 0 : TW_MID;
+            const cx<T>* __restrict__ tw = table + OFF + k;
             FCD_UNROLL
             for (int a = 0; a < R; ++a) {
                 cx<T> val = s[fft_pos(i + a * (L / R))];
