@@ -52,6 +52,7 @@ template <int L, int G, int DIR, class T>
 struct GenRows : NoPrologue {
     using F = Fft<L, DIR, T>;
     using Params = GenRowsParams<T>;
+    static constexpr int MIN_BLOCKS = 1;
     static constexpr int TPF = L / 16, THREADS = G * TPF, PHASES = 4;
     static constexpr int STRIDE = L + L / 16;
     static constexpr int SMEM_BYTES = G * STRIDE * (int)sizeof(cx<T>);
@@ -104,6 +105,7 @@ template <int L, int G, int DIR, class T>
 struct GenCols : NoPrologue {
     using F = Fft<L, DIR, T>;
     using Params = GenColsParams<T>;
+    static constexpr int MIN_BLOCKS = 1;
     static constexpr int TPF = L / 16, THREADS = G * TPF, PHASES = 4;
     static constexpr int STRIDE = L + L / 16;
     static constexpr int SMEM_BYTES = G * STRIDE * (int)sizeof(cx<T>);
@@ -144,6 +146,7 @@ struct SumParams {
 };
 struct SumKernel : NoPrologue {
     using Params = SumParams;
+    static constexpr int MIN_BLOCKS = 1;
     static constexpr int THREADS = 256, PHASES = 2, SMEM_BYTES = THREADS * (int)sizeof(double);
     struct State { int dummy; };
     template <int PH>
@@ -178,6 +181,7 @@ struct SpecMagParams {
 };
 struct SpecMag : NoPrologue {
     using Params = SpecMagParams;
+    static constexpr int MIN_BLOCKS = 1;
     static constexpr int THREADS = 256, PHASES = 1, SMEM_BYTES = 16;
     struct State { int dummy; };
     template <int PH>
@@ -209,6 +213,7 @@ struct CandidatesParams {
 };
 struct Candidates : NoPrologue {
     using Params = CandidatesParams;
+    static constexpr int MIN_BLOCKS = 1;
     static constexpr int THREADS = 256, PHASES = 1, SMEM_BYTES = 16;
     struct State { int dummy; };
     template <int PH>
@@ -238,6 +243,7 @@ struct MaskMulParams {
 };
 struct MaskMul : NoPrologue {
     using Params = MaskMulParams;
+    static constexpr int MIN_BLOCKS = 1;
     static constexpr int THREADS = 256, PHASES = 1, SMEM_BYTES = 16;
     struct State { int dummy; };
     template <int PH>
@@ -260,11 +266,13 @@ struct CcsgnStoreParams {
     const cd* g;
     cf* out_f;    // [H][W] complex64 (pipeline copy)
     cd* out_d;    // optional complex128 copy
+    float* theta; // optional angle(ccsgn) as float32 (what the demodulation kernel reads)
     long long n;
     int nblocks;
 };
 struct CcsgnStore : NoPrologue {
     using Params = CcsgnStoreParams;
+    static constexpr int MIN_BLOCKS = 1;
     static constexpr int THREADS = 256, PHASES = 1, SMEM_BYTES = 16;
     struct State { int dummy; };
     template <int PH>
@@ -273,6 +281,7 @@ struct CcsgnStore : NoPrologue {
             const cd z = conj(p.g[i]);
             if (p.out_f) p.out_f[i] = mk<float>((float)z.x, (float)z.y);
             if (p.out_d) p.out_d[i] = z;
+            if (p.theta) p.theta[i] = (float)atan2(z.y, z.x);
         }
     }
 };

@@ -111,6 +111,7 @@ struct RowFwd {
     using F = Fft<L, -1, float>;
     using GL = GroupLayout<L, G>;
     using Params = RowFwdParams;
+    static constexpr int MIN_BLOCKS = ((G * L / 16) <= 256 ? 3 : 1);
     static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 6;
     using TW = SmemTwiddles<F, THREADS>;
     static constexpr int SMEM_BYTES = TW::TW_BYTES + G * GL::STRIDE * (int)sizeof(cf);
@@ -199,7 +200,8 @@ struct ColBand {
     using FI = Fft<L, +1, float>;
     using GL = GroupLayout<L, G>;
     using Params = ColBandParams;
-    static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 10;
+    static constexpr int MIN_BLOCKS = ((G * L / 16) <= 256 ? 2 : 1);
+    static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 8;
     using TW = SmemTwiddles<FF, THREADS>;
     static constexpr int SMEM_BYTES = TW::TW_BYTES + G * GL::STRIDE * (int)sizeof(cf);
     FCD_HD static void prologue(const Params& p, int tid, unsigned char* smem) { TW::load(p.tw, tid, smem); }
@@ -209,7 +211,7 @@ struct ColBand {
     FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem_all, State& st) {
         const cf* tw = reinterpret_cast<const cf*>(smem_all);
         unsigned char* smem = smem_all + TW::TW_BYTES;
-        const int g = tid / TPF, t = tid % TPF;
+        const int g = tid % G, t = tid / G;   // group fastest: a warp covers 32/G rows x G columns
         cf* s = reinterpret_cast<cf*>(smem) + g * GL::STRIDE;
         const int H = L;
         const int i = by & 1;
@@ -244,17 +246,12 @@ struct ColBand {
             FI::stepB(st.v, t, s, tw);
         } else if constexpr (PH == 6) {
             FI::stepC(st.v, t, s);
-        } else if constexpr (PH == 7) {
-            FI::stepD(st.v, t, s, tw);
-        } else if constexpr (PH == 8) {
-            FCD_UNROLL
-            for (int m = 0; m < 16; ++m) s[fft_pos(t + TPF * m)] = st.v[m];
         } else {
-            const cf* sb = reinterpret_cast<const cf*>(smem);
-            for (int item = tid; item < G * H; item += THREADS) {
-                const int gg = item % G, y = item / G;
-                const int cc = bx * G + gg;
-                if (cc < p.nc[i]) p.w2[((long long)by * H + y) * p.ncp + cc] = sb[gg * GL::STRIDE + fft_pos(y)];
+            FI::stepD(st.v, t, s, tw);
+            if (c < p.nc[i]) {   // lanes: G adjacent columns x 32/G adjacent rows -> full sectors
+                cf* o = p.w2 + (long long)by * H * p.ncp + c;
+                FCD_UNROLL
+                for (int m = 0; m < 16; ++m) o[(long long)(t + TPF * m) * p.ncp] = st.v[m];
             }
         }
     }
@@ -269,7 +266,7 @@ struct ColBand {
 // =========================================================================================
 struct RowDemodParams {
     const cf* w2;
-    const cf* ccsgn;     // [2][H][W]
+    const float* theta;  // [2][H][W]  angle(ccsgn) of the bound reference
     cf* w3;              // [F][H][W]
     float* colphase;     // [F][2][H]
     float* phases;       // [F][2][H][W] or null
@@ -289,6 +286,7 @@ struct RowDemod {
     using FI = Fft<L, +1, float>;
     using GL = GroupLayout<L, G>;
     using Params = RowDemodParams;
+    static constexpr int MIN_BLOCKS = ((G * L / 16) <= 256 ? 2 : 1);
     static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 18;
     // per group: exchange buffer (aliased by the jump scan), chunk totals, chunk offsets, flag
     static constexpr int AUX_INTS = 4 * TPF + 4;
@@ -314,14 +312,15 @@ struct RowDemod {
     }
     FCD_HD static void demod(const Params& p, int i, int y, int t, const cf* v, float* ph) {
         const int W = L;
-        const cf* __restrict__ cc = p.ccsgn + ((long long)i * p.H + y) * W;
-        cf c[16];
+        // -angle(g * ccsgn) = -wrap(angle(g) + angle(ccsgn))           (fcd.py:118)
+        const float* __restrict__ th = p.theta + ((long long)i * p.H + y) * W;
+        float c[16];
         FCD_UNROLL
-        for (int m = 0; m < 16; ++m) c[m] = cc[t + TPF * m];     // all loads in flight first
+        for (int m = 0; m < 16; ++m) c[m] = th[t + TPF * m];     // all loads in flight first
         FCD_UNROLL
         for (int m = 0; m < 16; ++m) {
-            const cf q = v[m] * c[m];
-            ph[m] = -fast_atan2f(q.y, q.x);
+            const float a = fast_atan2f(v[m].y, v[m].x) + c[m];
+            ph[m] = kTwoPiF * rintf(a * kInvTwoPiF) - a;
         }
     }
 
@@ -476,6 +475,7 @@ struct RowLinkParams {
 
 struct RowLink : NoPrologue {
     using Params = RowLinkParams;
+    static constexpr int MIN_BLOCKS = 1;
     static constexpr int THREADS = 256, PHASES = 4;
     static constexpr int MAXH = 4096;
     static constexpr int SMEM_BYTES = (MAXH + 2 * THREADS + 4) * (int)sizeof(int);
@@ -525,6 +525,7 @@ struct PhaseFixParams {
 };
 struct PhaseFix : NoPrologue {
     using Params = PhaseFixParams;
+    static constexpr int MIN_BLOCKS = 1;
     static constexpr int THREADS = 256, PHASES = 1, SMEM_BYTES = 16;
     struct State { int dummy; };
     template <int PH>
@@ -564,7 +565,8 @@ struct ColIntegrate {
     using FI = Fft<L, +1, float>;
     using GL = GroupLayout<L, G>;
     using Params = ColIntegrateParams;
-    static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 16;
+    static constexpr int MIN_BLOCKS = 1;
+    static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 14;
     using TW = SmemTwiddles<FF, THREADS>;
     static constexpr int SMEM_BYTES = TW::TW_BYTES + G * GL::STRIDE * (int)sizeof(cf);
     FCD_HD static void prologue(const Params& p, int tid, unsigned char* smem) { TW::load(p.tw, tid, smem); }
@@ -591,7 +593,7 @@ struct ColIntegrate {
     FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem_all, State& st) {
         const cf* tw = reinterpret_cast<const cf*>(smem_all);
         unsigned char* smem = smem_all + TW::TW_BYTES;
-        const int g = tid / TPF, t = tid % TPF;
+        const int g = tid % G, t = tid / G;   // group fastest: a warp covers 32/G rows x G columns
         cf* s = reinterpret_cast<cf*>(smem) + g * GL::STRIDE;
         const int H = L;
         const int f = by;
@@ -659,17 +661,12 @@ struct ColIntegrate {
             FI::stepB(st.v, t, s, tw);
         } else if constexpr (PH == 12) {
             FI::stepC(st.v, t, s);
-        } else if constexpr (PH == 13) {
-            FI::stepD(st.v, t, s, tw);
-        } else if constexpr (PH == 14) {
-            FCD_UNROLL
-            for (int m = 0; m < 16; ++m) s[fft_pos(t + TPF * m)] = st.v[m];
         } else {
-            const cf* sb = reinterpret_cast<const cf*>(smem);
-            for (int item = tid; item < G * H; item += THREADS) {
-                const int gg = item % G, y = item / G;
-                const int kk = bx * G + gg;
-                if (kk <= p.W / 2) p.w4[((long long)f * H + y) * p.w4p + kk] = sb[gg * GL::STRIDE + fft_pos(y)];
+            FI::stepD(st.v, t, s, tw);
+            if (valid) {
+                cf* o = p.w4 + (long long)f * H * p.w4p + kc;
+                FCD_UNROLL
+                for (int m = 0; m < 16; ++m) o[(long long)(t + TPF * m) * p.w4p] = st.v[m];
             }
         }
     }
@@ -692,6 +689,7 @@ struct RowInv {
     using FI = Fft<L, +1, float>;
     using GL = GroupLayout<L, G>;
     using Params = RowInvParams;
+    static constexpr int MIN_BLOCKS = ((G * L / 16) <= 256 ? 3 : 1);
     static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 4;
     using TW = SmemTwiddles<FI, THREADS>;
     static constexpr int SMEM_BYTES = TW::TW_BYTES + G * GL::STRIDE * (int)sizeof(cf);

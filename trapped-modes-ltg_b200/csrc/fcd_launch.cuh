@@ -95,7 +95,7 @@ __device__ __forceinline__ void run_phases(const typename K::Params& p, int bx, 
 // Persistent blocks: grid = min(tiles, SMs * resident blocks per SM); each block runs the
 // prologue once (twiddle table -> shared memory) and then loops over tiles (bx, by).
 template <class K>
-__global__ void __launch_bounds__(K::THREADS) fcd_kernel(const __grid_constant__ typename K::Params p, int gx, int ntiles) {
+__global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) fcd_kernel(const __grid_constant__ typename K::Params p, int gx, int ntiles) {
     extern __shared__ __align__(16) unsigned char fcd_smem[];
     typename K::State st;
     K::prologue(p, (int)threadIdx.x, fcd_smem);

@@ -68,7 +68,8 @@ struct PlanImpl {
     int c_lo[2] = {0, 0}, nc[2] = {0, 0}, ncp = 4;
     std::vector<int> h_lo, h_hi;           // [2][ncp]
     rt::DevBuf<int> chord_lo, chord_hi;
-    rt::DevBuf<cf> ccsgn;                  // [2][H][W]
+    rt::DevBuf<cf> ccsgn;                  // [2][H][W] complex64 copy (Carrier.ccsgn)
+    rt::DevBuf<float> theta;               // [2][H][W] angle(ccsgn), read by the demodulation kernel
     rt::DevBuf<float> kx, kxq;
     float dky = 0.f;
     double f[2][2] = {{0, 0}, {0, 0}};     // carrier wavevectors [k_row, k_col]
@@ -340,10 +341,12 @@ struct PlanImpl {
         spec_valid = true;
         const long long n = (long long)H * W;
         ccsgn.alloc((size_t)2 * n);
+        theta.alloc((size_t)2 * n);
         for (int i = 0; i < 2; ++i) {
             masked_inverse(i, s, nullptr);
             const int nb = elem_blocks(n);
-            launch<CcsgnStore>(nb, 1, s, CcsgnStoreParams{tmp.ptr, ccsgn.ptr + (size_t)i * n, nullptr, n, nb});
+            launch<CcsgnStore>(nb, 1, s, CcsgnStoreParams{tmp.ptr, ccsgn.ptr + (size_t)i * n, nullptr,
+                                                         theta.ptr + (size_t)i * n, n, nb});
         }
 
         // workspaces
@@ -389,7 +392,7 @@ struct PlanImpl {
             if (profiling) timer.mark(s, 1);
             FCD_DISPATCH_L(W, {
                 constexpr int G = Tune<L>::GDEM;
-                RowDemodParams p{w2.ptr, ccsgn.ptr, w3.ptr, colphase.ptr, po, tw_w_f.ptr, H, ncp,
+                RowDemodParams p{w2.ptr, theta.ptr, w3.ptr, colphase.ptr, po, tw_w_f.ptr, H, ncp,
                                  {nc[0], nc[1]}, {c_lo[0] - W / 2, c_lo[1] - W / 2}, W / 2, unwrap ? 1 : 0};
                 launch<RowDemod<L, G>>(nf, H / G, s, p);
             })
@@ -556,7 +559,7 @@ int fcd_get_carrier_ccsgn(fcd_plan* plan, int carrier, void* ccsgn_dev, int as_c
         im.masked_inverse(carrier, stream, nullptr);
         const int nb = fcd::PlanImpl::elem_blocks(n);
         im.launch<fcd::CcsgnStore>(nb, 1, stream,
-                                   fcd::CcsgnStoreParams{im.tmp.ptr, nullptr, static_cast<fcd::cd*>(ccsgn_dev), n, nb});
+                                   fcd::CcsgnStoreParams{im.tmp.ptr, nullptr, static_cast<fcd::cd*>(ccsgn_dev), nullptr, n, nb});
     });
 }
 
