@@ -52,6 +52,7 @@ template <int L, int G, int DIR, class T>
 struct GenRows : NoPrologue {
     using F = Fft<L, DIR, T>;
     using Params = GenRowsParams<T>;
+    static constexpr bool BLOCKED_TILES = false;
     static constexpr int MIN_BLOCKS = 1;
     static constexpr int TPF = L / 16, THREADS = G * TPF, PHASES = 4;
     static constexpr int STRIDE = L + L / 16;
@@ -105,6 +106,7 @@ template <int L, int G, int DIR, class T>
 struct GenCols : NoPrologue {
     using F = Fft<L, DIR, T>;
     using Params = GenColsParams<T>;
+    static constexpr bool BLOCKED_TILES = false;
     static constexpr int MIN_BLOCKS = 1;
     static constexpr int TPF = L / 16, THREADS = G * TPF, PHASES = 4;
     static constexpr int STRIDE = L + L / 16;
@@ -146,6 +148,7 @@ struct SumParams {
 };
 struct SumKernel : NoPrologue {
     using Params = SumParams;
+    static constexpr bool BLOCKED_TILES = false;
     static constexpr int MIN_BLOCKS = 1;
     static constexpr int THREADS = 256, PHASES = 2, SMEM_BYTES = THREADS * (int)sizeof(double);
     struct State { int dummy; };
@@ -181,6 +184,7 @@ struct SpecMagParams {
 };
 struct SpecMag : NoPrologue {
     using Params = SpecMagParams;
+    static constexpr bool BLOCKED_TILES = false;
     static constexpr int MIN_BLOCKS = 1;
     static constexpr int THREADS = 256, PHASES = 1, SMEM_BYTES = 16;
     struct State { int dummy; };
@@ -213,6 +217,7 @@ struct CandidatesParams {
 };
 struct Candidates : NoPrologue {
     using Params = CandidatesParams;
+    static constexpr bool BLOCKED_TILES = false;
     static constexpr int MIN_BLOCKS = 1;
     static constexpr int THREADS = 256, PHASES = 1, SMEM_BYTES = 16;
     struct State { int dummy; };
@@ -243,6 +248,7 @@ struct MaskMulParams {
 };
 struct MaskMul : NoPrologue {
     using Params = MaskMulParams;
+    static constexpr bool BLOCKED_TILES = false;
     static constexpr int MIN_BLOCKS = 1;
     static constexpr int THREADS = 256, PHASES = 1, SMEM_BYTES = 16;
     struct State { int dummy; };
@@ -272,6 +278,7 @@ struct CcsgnStoreParams {
 };
 struct CcsgnStore : NoPrologue {
     using Params = CcsgnStoreParams;
+    static constexpr bool BLOCKED_TILES = false;
     static constexpr int MIN_BLOCKS = 1;
     static constexpr int THREADS = 256, PHASES = 1, SMEM_BYTES = 16;
     struct State { int dummy; };

@@ -62,13 +62,14 @@ FCD_HD float fast_atan2f(float y, float x) {
 }
 
 // common helpers -------------------------------------------------------------------------
-template <int L, int G>
+template <int L, int G, int BUFS = 1>
 struct GroupLayout {
     static constexpr int TPF = L / 16;
     static constexpr int THREADS = G * TPF;
-    // per-group exchange buffer; the skew makes "lane = group" accesses conflict free
-    static constexpr int SKEW = (G > 1 && G <= 16) ? 16 / G : 0;
-    static constexpr int STRIDE = L + L / 16 + SKEW;  // elements
+    // per-group exchange buffer(s); the skew spreads "lane = group" accesses over the banks
+    static constexpr int SKEW = (G * BUFS > 1 && G * BUFS <= 16) ? 16 / (G * BUFS) : (G * BUFS > 16 ? 1 : 0);
+    static constexpr int STRIDE = L + L / 16 + SKEW;  // elements per buffer
+    static constexpr int GROUP_STRIDE = BUFS * STRIDE;
 };
 
 struct alignas(16) cf2 {
@@ -111,6 +112,7 @@ struct RowFwd {
     using F = Fft<L, -1, float>;
     using GL = GroupLayout<L, G>;
     using Params = RowFwdParams;
+    static constexpr bool BLOCKED_TILES = false;
     static constexpr int MIN_BLOCKS = ((G * L / 16) <= 256 ? 3 : 1);
     static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 6;
     using TW = SmemTwiddles<F, THREADS>;
@@ -200,6 +202,7 @@ struct ColBand {
     using FI = Fft<L, +1, float>;
     using GL = GroupLayout<L, G>;
     using Params = ColBandParams;
+    static constexpr bool BLOCKED_TILES = false;
     static constexpr int MIN_BLOCKS = ((G * L / 16) <= 256 ? 2 : 1);
     static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 8;
     using TW = SmemTwiddles<FF, THREADS>;
@@ -284,19 +287,21 @@ template <int L, int G>
 struct RowDemod {
     using FF = Fft<L, -1, float>;
     using FI = Fft<L, +1, float>;
-    using GL = GroupLayout<L, G>;
+    using GL = GroupLayout<L, G, 2>;
     using Params = RowDemodParams;
+    static constexpr bool BLOCKED_TILES = true;
     static constexpr int MIN_BLOCKS = ((G * L / 16) <= 256 ? 2 : 1);
-    static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 18;
-    // per group: exchange buffer (aliased by the jump scan), chunk totals, chunk offsets, flag
-    static constexpr int AUX_INTS = 4 * TPF + 4;
-    static constexpr int GROUP_BYTES = GL::STRIDE * (int)sizeof(cf) + AUX_INTS * (int)sizeof(int);
+    static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 12;
     using TW = SmemTwiddles<FF, THREADS>;
+    // per group: two exchange buffers (one per carrier; the second doubles as the jump-scan
+    // array), chunk totals, chunk offsets, flag
+    static constexpr int AUX_INTS = 4 * TPF + 4;
+    static constexpr int GROUP_BYTES = GL::GROUP_STRIDE * (int)sizeof(cf) + AUX_INTS * (int)sizeof(int);
     static constexpr int SMEM_BYTES = TW::TW_BYTES + G * GROUP_BYTES;
     FCD_HD static void prologue(const Params& p, int tid, unsigned char* smem) { TW::load(p.tw, tid, smem); }
     struct State {
-        cf v[16];
-        float ph0[16], ph1[16];
+        cf v[16];   // carrier 0, later (phi0, phi1)
+        cf w[16];   // carrier 1, later the row jumps
     };
 
     FCD_HD static void load_band(const Params& p, int f, int i, int y, int t, cf* v) {
@@ -310,9 +315,9 @@ struct RowDemod {
             v[m] = (c >= 0 && c < p.nc[i]) ? row[c] : mk<float>(0.f, 0.f);
         }
     }
+    // -angle(g * ccsgn) = -wrap(angle(g) + angle(ccsgn))           (fcd.py:118)
     FCD_HD static void demod(const Params& p, int i, int y, int t, const cf* v, float* ph) {
         const int W = L;
-        // -angle(g * ccsgn) = -wrap(angle(g) + angle(ccsgn))           (fcd.py:118)
         const float* __restrict__ th = p.theta + ((long long)i * p.H + y) * W;
         float c[16];
         FCD_UNROLL
@@ -324,85 +329,75 @@ struct RowDemod {
         }
     }
 
+    // Both carriers of a row are transformed together (shared twiddle loads, half the barriers).
     template <int PH>
     FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem_all, State& st) {
         const cf* tw = reinterpret_cast<const cf*>(smem_all);
         unsigned char* smem = smem_all + TW::TW_BYTES;
         const int g = tid / TPF, t = tid % TPF;
         unsigned char* gbase = smem + (size_t)g * GROUP_BYTES;
-        cf* s = reinterpret_cast<cf*>(gbase);
-        int2s* sj = reinterpret_cast<int2s*>(gbase);  // aliases s (L + L/16 int2 <= buffer)
-        int* aux = reinterpret_cast<int*>(gbase + GL::STRIDE * sizeof(cf));
+        cf* s0 = reinterpret_cast<cf*>(gbase);
+        cf* s1 = s0 + GL::STRIDE;
+        int2s* sj = reinterpret_cast<int2s*>(s1);               // jump scan array lives in buffer 1
+        int* aux = reinterpret_cast<int*>(gbase + GL::GROUP_STRIDE * sizeof(cf));
         int2s* part = reinterpret_cast<int2s*>(aux);            // [TPF]
         int2s* off = reinterpret_cast<int2s*>(aux + 2 * TPF);   // [TPF]
         int* flag = aux + 4 * TPF;
         const int W = L;
         const int y = by * G + g;   // tiles are ordered frame-fastest so that consecutive tiles of
-        const int f = bx;           // a block reuse the same ccsgn rows out of L2
+        const int f = bx;           // a block reuse the same theta rows out of L2
         if constexpr (PH == 0) {
             if (t == 0) *flag = 0;
             load_band(p, f, 0, y, t, st.v);
-            FI::stepA(st.v, t, s);
+            load_band(p, f, 1, y, t, st.w);
+            FI::stepA(st.v, t, s0);
+            FI::stepA(st.w, t, s1);
         } else if constexpr (PH == 1) {
-            FI::stepB(st.v, t, s, tw);
+            FI::stepB2(st.v, st.w, t, s0, s1, tw);
         } else if constexpr (PH == 2) {
-            FI::stepC(st.v, t, s);
+            FI::stepC(st.v, t, s0);
+            FI::stepC(st.w, t, s1);
         } else if constexpr (PH == 3) {
-            FI::stepD(st.v, t, s, tw);
-            demod(p, 0, y, t, st.v, st.ph0);
-        } else if constexpr (PH == 4) {
-            load_band(p, f, 1, y, t, st.v);
-            FI::stepA(st.v, t, s);
-        } else if constexpr (PH == 5) {
-            FI::stepB(st.v, t, s, tw);
-        } else if constexpr (PH == 6) {
-            FI::stepC(st.v, t, s);
-        } else if constexpr (PH == 7) {
-            FI::stepD(st.v, t, s, tw);
-            demod(p, 1, y, t, st.v, st.ph1);
-            // wrapped phase at the anchor column links the rows (K3b)
+            FI::stepD2(st.v, st.w, t, s0, s1, tw);
+            float ph0[16], ph1[16];
+            demod(p, 0, y, t, st.v, ph0);
+            demod(p, 1, y, t, st.w, ph1);
+            FCD_UNROLL
+            for (int m = 0; m < 16; ++m) st.v[m] = mk<float>(ph0[m], ph1[m]);
+            // wrapped phase at the anchor column links the rows (RowLink)
             if (t == (p.x_ref % TPF)) {
-                const int m = p.x_ref / TPF;
-                float a0 = 0.f, a1 = 0.f;
+                const int mr = p.x_ref / TPF;
+                cf a = mk<float>(0.f, 0.f);
                 FCD_UNROLL
                 for (int mm = 0; mm < 16; ++mm)
-                    if (mm == m) { a0 = st.ph0[mm]; a1 = st.ph1[mm]; }
-                p.colphase[((long long)f * 2 + 0) * p.H + y] = a0;
-                p.colphase[((long long)f * 2 + 1) * p.H + y] = a1;
+                    if (mm == mr) a = st.v[mm];
+                p.colphase[((long long)f * 2 + 0) * p.H + y] = a.x;
+                p.colphase[((long long)f * 2 + 1) * p.H + y] = a.y;
             }
-        } else if constexpr (PH == 8) {
+        } else if constexpr (PH == 4) {
             if (p.unwrap) {
                 FCD_UNROLL
-                for (int m = 0; m < 16; ++m) s[fft_pos(t + TPF * m)] = mk<float>(st.ph0[m], st.ph1[m]);
+                for (int m = 0; m < 16; ++m) s0[fft_pos(t + TPF * m)] = st.v[m];
             }
-        } else if constexpr (PH == 9) {
-            // jumps to the left neighbour; kept in v (as ints) until the buffer may be reused
+        } else if constexpr (PH == 5) {
+            // 2*pi jumps to the left neighbour -> buffer 1 (as integers)
             if (p.unwrap) {
                 bool any = false;
                 FCD_UNROLL
                 for (int m = 0; m < 16; ++m) {
                     const int x = t + TPF * m;
-                    int j0 = 0, j1 = 0;
+                    int2s j; j.a = 0; j.b = 0;
                     if (x > 0) {
-                        const cf prev = s[fft_pos(x - 1)];
-                        j0 = (int)rintf((st.ph0[m] - prev.x) * kInvTwoPiF);
-                        j1 = (int)rintf((st.ph1[m] - prev.y) * kInvTwoPiF);
+                        const cf prev = s0[fft_pos(x - 1)];
+                        j.a = (int)rintf((st.v[m].x - prev.x) * kInvTwoPiF);
+                        j.b = (int)rintf((st.v[m].y - prev.y) * kInvTwoPiF);
                     }
-                    any = any || (j0 != 0) || (j1 != 0);
-                    st.v[m].x = (float)j0;
-                    st.v[m].y = (float)j1;
+                    any = any || (j.a != 0) || (j.b != 0);
+                    sj[fft_pos(x)] = j;
                 }
                 if (any) *flag = 1;
             }
-        } else if constexpr (PH == 10) {
-            if (p.unwrap && *flag) {
-                FCD_UNROLL
-                for (int m = 0; m < 16; ++m) {
-                    int2s j; j.a = (int)st.v[m].x; j.b = (int)st.v[m].y;
-                    sj[fft_pos(t + TPF * m)] = j;
-                }
-            }
-        } else if constexpr (PH == 11) {
+        } else if constexpr (PH == 6) {
             if (p.unwrap && *flag) {   // inclusive scan of this thread's contiguous chunk
                 int a = 0, b = 0;
                 FCD_UNROLL
@@ -415,14 +410,14 @@ struct RowDemod {
                 int2s tot; tot.a = a; tot.b = b;
                 part[t] = tot;
             }
-        } else if constexpr (PH == 12) {
+        } else if constexpr (PH == 7) {
             if (p.unwrap && *flag) {
                 int a = 0, b = 0;
                 for (int q = 0; q < t; ++q) { a += part[q].a; b += part[q].b; }
                 int2s o; o.a = a; o.b = b;
                 off[t] = o;
             }
-        } else if constexpr (PH == 13) {
+        } else if constexpr (PH == 8) {
             if (p.unwrap && *flag) {
                 const int2s cr = sj[fft_pos(p.x_ref)];
                 const int2s orf = off[p.x_ref >> 4];
@@ -432,8 +427,8 @@ struct RowDemod {
                     const int x = t + TPF * m;
                     const int2s c = sj[fft_pos(x)];
                     const int2s o = off[x >> 4];
-                    st.ph0[m] -= kTwoPiF * (float)(c.a + o.a - ra);
-                    st.ph1[m] -= kTwoPiF * (float)(c.b + o.b - rb);
+                    st.v[m].x -= kTwoPiF * (float)(c.a + o.a - ra);
+                    st.v[m].y -= kTwoPiF * (float)(c.b + o.b - rb);
                 }
             }
             if (p.phases) {
@@ -441,26 +436,24 @@ struct RowDemod {
                 float* o1 = p.phases + (((long long)f * 2 + 1) * p.H + y) * W;
                 FCD_UNROLL
                 for (int m = 0; m < 16; ++m) {
-                    o0[t + TPF * m] = st.ph0[m];
-                    o1[t + TPF * m] = st.ph1[m];
+                    o0[t + TPF * m] = st.v[m].x;
+                    o1[t + TPF * m] = st.v[m].y;
                 }
             }
-            FCD_UNROLL
-            for (int m = 0; m < 16; ++m) st.v[m] = mk<float>(st.ph0[m], st.ph1[m]);
-        } else if constexpr (PH == 14) {
-            FF::stepA(st.v, t, s);
-        } else if constexpr (PH == 15) {
-            FF::stepB(st.v, t, s, tw);
-        } else if constexpr (PH == 16) {
-            FF::stepC(st.v, t, s);
+            FF::stepA(st.v, t, s0);
+        } else if constexpr (PH == 9) {
+            FF::stepB(st.v, t, s0, tw);
+        } else if constexpr (PH == 10) {
+            FF::stepC(st.v, t, s0);
         } else {
-            FF::stepD(st.v, t, s, tw);
+            FF::stepD(st.v, t, s0, tw);
             cf* o = p.w3 + ((long long)f * p.H + y) * W;
             FCD_UNROLL
             for (int m = 0; m < 16; ++m) o[t + TPF * m] = st.v[m];
         }
     }
 };
+
 
 // =========================================================================================
 // K3b row linking: integer prefix sum along y of the 2pi jumps of the anchor column.
@@ -475,6 +468,7 @@ struct RowLinkParams {
 
 struct RowLink : NoPrologue {
     using Params = RowLinkParams;
+    static constexpr bool BLOCKED_TILES = false;
     static constexpr int MIN_BLOCKS = 1;
     static constexpr int THREADS = 256, PHASES = 4;
     static constexpr int MAXH = 4096;
@@ -525,6 +519,7 @@ struct PhaseFixParams {
 };
 struct PhaseFix : NoPrologue {
     using Params = PhaseFixParams;
+    static constexpr bool BLOCKED_TILES = false;
     static constexpr int MIN_BLOCKS = 1;
     static constexpr int THREADS = 256, PHASES = 1, SMEM_BYTES = 16;
     struct State { int dummy; };
@@ -563,12 +558,13 @@ template <int L, int G>
 struct ColIntegrate {
     using FF = Fft<L, -1, float>;
     using FI = Fft<L, +1, float>;
-    using GL = GroupLayout<L, G>;
+    using GL = GroupLayout<L, G, 2>;
     using Params = ColIntegrateParams;
+    static constexpr bool BLOCKED_TILES = false;
     static constexpr int MIN_BLOCKS = 1;
-    static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 14;
+    static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 9;
     using TW = SmemTwiddles<FF, THREADS>;
-    static constexpr int SMEM_BYTES = TW::TW_BYTES + G * GL::STRIDE * (int)sizeof(cf);
+    static constexpr int SMEM_BYTES = TW::TW_BYTES + G * GL::GROUP_STRIDE * (int)sizeof(cf);
     FCD_HD static void prologue(const Params& p, int tid, unsigned char* smem) { TW::load(p.tw, tid, smem); }
     struct State { cf v[16]; cf va[16]; };
 
@@ -589,50 +585,48 @@ struct ColIntegrate {
         }
     }
 
+    // Both columns of a conjugate pair (kc, W-kc) are transformed together: one exposure of the
+    // global-load latency per tile and every twiddle is loaded once for the two transforms.
     template <int PH>
     FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem_all, State& st) {
         const cf* tw = reinterpret_cast<const cf*>(smem_all);
         unsigned char* smem = smem_all + TW::TW_BYTES;
         const int g = tid % G, t = tid / G;   // group fastest: a warp covers 32/G rows x G columns
-        cf* s = reinterpret_cast<cf*>(smem) + g * GL::STRIDE;
+        cf* s0 = reinterpret_cast<cf*>(smem) + g * GL::GROUP_STRIDE;   // column kc, later the inverse
+        cf* s1 = s0 + GL::STRIDE;                                        // column W-kc
         const int H = L;
         const int f = by;
         const int kc = bx * G + g;
         const bool valid = kc <= p.W / 2;
         const int kcm = (p.W - kc) & (p.W - 1);
         if constexpr (PH == 0) {
-            if (valid) load_col(p, f, kc, t, st.v);
-            else { FCD_UNROLL for (int m = 0; m < 16; ++m) st.v[m] = mk<float>(0.f, 0.f); }
-            FF::stepA(st.v, t, s);
+            if (valid) {
+                load_col(p, f, kc, t, st.va);
+                load_col(p, f, kcm, t, st.v);
+            } else {
+                FCD_UNROLL
+                for (int m = 0; m < 16; ++m) { st.va[m] = mk<float>(0.f, 0.f); st.v[m] = mk<float>(0.f, 0.f); }
+            }
+            FF::stepA(st.va, t, s0);
+            FF::stepA(st.v, t, s1);
         } else if constexpr (PH == 1) {
-            FF::stepB(st.v, t, s, tw);
+            FF::stepB2(st.va, st.v, t, s0, s1, tw);
         } else if constexpr (PH == 2) {
-            FF::stepC(st.v, t, s);
+            FF::stepC(st.va, t, s0);
+            FF::stepC(st.v, t, s1);
         } else if constexpr (PH == 3) {
-            FF::stepD(st.v, t, s, tw);
-            FCD_UNROLL
-            for (int m = 0; m < 16; ++m) st.va[m] = st.v[m];
+            FF::stepD2(st.va, st.v, t, s0, s1, tw);
         } else if constexpr (PH == 4) {
-            if (valid) load_col(p, f, kcm, t, st.v);
-            else { FCD_UNROLL for (int m = 0; m < 16; ++m) st.v[m] = mk<float>(0.f, 0.f); }
-            FF::stepA(st.v, t, s);
-        } else if constexpr (PH == 5) {
-            FF::stepB(st.v, t, s, tw);
-        } else if constexpr (PH == 6) {
-            FF::stepC(st.v, t, s);
-        } else if constexpr (PH == 7) {
-            FF::stepD(st.v, t, s, tw);
-        } else if constexpr (PH == 8) {
             FCD_UNROLL
-            for (int m = 0; m < 16; ++m) s[fft_pos(t + TPF * m)] = st.v[m];
-        } else if constexpr (PH == 9) {
+            for (int m = 0; m < 16; ++m) s1[fft_pos(t + TPF * m)] = st.v[m];   // Z(., W-kc), natural order
+        } else if constexpr (PH == 5) {
             if (valid) {
                 const float kxv = p.kx[kc], kxa = p.kxq[kc], kxb = p.kxq[kcm];
                 FCD_UNROLL
                 for (int m = 0; m < 16; ++m) {
                     const int kr = t + TPF * m;
                     const int krm = (H - kr) & (H - 1);
-                    const cf zm = conj(s[fft_pos(krm)]);       // conj Z(-kr, -kc)
+                    const cf zm = conj(s1[fft_pos(krm)]);      // conj Z(-kr, -kc)
                     const cf z = st.va[m];                      // Z(kr, kc)
                     const cf p0 = z + zm;                       // 2 * Phi0(k)
                     const cf p1 = mul_mi(z - zm);               // 2 * Phi1(k)
@@ -655,14 +649,13 @@ struct ColIntegrate {
                 FCD_UNROLL
                 for (int m = 0; m < 16; ++m) st.v[m] = mk<float>(0.f, 0.f);
             }
-        } else if constexpr (PH == 10) {
-            FI::stepA(st.v, t, s);
-        } else if constexpr (PH == 11) {
-            FI::stepB(st.v, t, s, tw);
-        } else if constexpr (PH == 12) {
-            FI::stepC(st.v, t, s);
+            FI::stepA(st.v, t, s0);
+        } else if constexpr (PH == 6) {
+            FI::stepB(st.v, t, s0, tw);
+        } else if constexpr (PH == 7) {
+            FI::stepC(st.v, t, s0);
         } else {
-            FI::stepD(st.v, t, s, tw);
+            FI::stepD(st.v, t, s0, tw);
             if (valid) {
                 cf* o = p.w4 + (long long)f * H * p.w4p + kc;
                 FCD_UNROLL
@@ -671,6 +664,7 @@ struct ColIntegrate {
         }
     }
 };
+
 
 // =========================================================================================
 // K5  row inverse (c2r, two rows per transform):  w4[f][y][0..W/2] -> height[f][y][x]
@@ -689,6 +683,7 @@ struct RowInv {
     using FI = Fft<L, +1, float>;
     using GL = GroupLayout<L, G>;
     using Params = RowInvParams;
+    static constexpr bool BLOCKED_TILES = false;
     static constexpr int MIN_BLOCKS = ((G * L / 16) <= 256 ? 3 : 1);
     static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 4;
     using TW = SmemTwiddles<FI, THREADS>;

@@ -202,6 +202,33 @@ struct Fft {
             }
         }
     }
+    // two independent transforms (same length, same direction) sharing each twiddle load
+    template <int R, int PP>
+    FCD_HD static void gather2(cx<T>* v0, cx<T>* v1, int t, const cx<T>* s0, const cx<T>* s1,
+                               const cx<T>* __restrict__ table) {
+        constexpr int NB = 16 / R;
+        FCD_UNROLL
+        for (int ii = 0; ii < NB; ++ii) {
+            const int i = t + TPF * ii;
+            const int k = i & (PP - 1);
+            constexpr int OFF = (THREE && PP == R1) ? 0 : TW_MID;
+            const cx<T>* __restrict__ tw = table + OFF + k;
+            FCD_UNROLL
+            for (int a = 0; a < R; ++a) {
+                const int pos = fft_pos(i + a * (L / R));
+                cx<T> x0 = s0[pos], x1 = s1[pos];
+                if (PP > 1 && a > 0) {
+                    cx<T> w = tw[a * PP];
+                    if (DIR > 0) w = conj(w);
+                    x0 = x0 * w;
+                    x1 = x1 * w;
+                }
+                v0[ii + NB * a] = x0;
+                v1[ii + NB * a] = x1;
+            }
+        }
+    }
+
     template <int R>
     FCD_HD static void butterflies(cx<T>* v) {
         constexpr int NB = 16 / R;
@@ -237,6 +264,16 @@ struct Fft {
             butterflies<R2>(v);
             scatter<R2, R1>(v, t, s);
         }
+    }
+    FCD_HD static void stepB2(cx<T>* v0, cx<T>* v1, int t, const cx<T>* s0, const cx<T>* s1,
+                              const cx<T>* __restrict__ table) {
+        if constexpr (THREE) gather2<R2, R1>(v0, v1, t, s0, s1, table);
+    }
+    FCD_HD static void stepD2(cx<T>* v0, cx<T>* v1, int t, const cx<T>* s0, const cx<T>* s1,
+                              const cx<T>* __restrict__ table) {
+        gather2<R3, R1 * R2>(v0, v1, t, s0, s1, table);
+        butterflies<R3>(v0);
+        butterflies<R3>(v1);
     }
     // D: smem -> last-pass butterflies -> v (natural ownership)
     FCD_HD static void stepD(cx<T>* v, int t, const cx<T>* s, const cx<T>* __restrict__ table) {
