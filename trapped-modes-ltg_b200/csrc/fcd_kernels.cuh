@@ -158,7 +158,7 @@ struct RowFwd {
             F::stepD(st.v, t, s, tw);
         } else if constexpr (PH == 4) {
             FCD_UNROLL
-            for (int m = 0; m < 16; ++m) s[fft_pos(t + TPF * m)] = st.v[m];
+            for (int m = 0; m < 16; ++m) s[fft_nat<TPF>(t, m)] = st.v[m];
         } else {
             const cf* sb = reinterpret_cast<const cf*>(smem);
             const int total = 2 * p.ncp * G;
@@ -377,7 +377,7 @@ struct RowDemod {
         } else if constexpr (PH == 4) {
             if (p.unwrap) {
                 FCD_UNROLL
-                for (int m = 0; m < 16; ++m) s0[fft_pos(t + TPF * m)] = st.v[m];
+                for (int m = 0; m < 16; ++m) s0[fft_nat<TPF>(t, m)] = st.v[m];
             }
         } else if constexpr (PH == 5) {
             // 2*pi jumps to the left neighbour -> buffer 1 (as integers)
@@ -618,7 +618,7 @@ struct ColIntegrate {
             FF::stepD2(st.va, st.v, t, s0, s1, tw);
         } else if constexpr (PH == 4) {
             FCD_UNROLL
-            for (int m = 0; m < 16; ++m) s1[fft_pos(t + TPF * m)] = st.v[m];   // Z(., W-kc), natural order
+            for (int m = 0; m < 16; ++m) s1[fft_nat<TPF>(t, m)] = st.v[m];   // Z(., W-kc), natural order
         } else if constexpr (PH == 5) {
             if (valid) {
                 const float kxv = p.kx[kc], kxa = p.kxq[kc], kxb = p.kxq[kcm];

@@ -150,6 +150,12 @@ template <> struct Plan<4096> { static constexpr int R1 = 16, R2 = 16, R3 = 16; 
 // smem slot of logical element p: one pad element per 16 (keeps radix-strided writes of
 // the first pass and 16-aligned runs of the later passes bank-conflict free)
 FCD_HD int fft_pos(int p) { return p + (p >> 4); }
+// padded offset of a multiple of 16 (exact: fft_pos(p + c) == fft_pos(p) + fft_padc(c) when c % 16 == 0)
+FCD_HD constexpr int fft_padc(int c) { return c + (c >> 4); }
+// slot of the m-th owned element t + TPF*m (natural strided ownership)
+template <int TPF> FCD_HD int fft_nat(int t, int m) {
+    return (TPF % 16 == 0) ? fft_pos(t) + fft_padc(TPF * m) : fft_pos(t + TPF * m);
+}
 
 template <int L, int DIR, class T, class P = Plan<L>>
 struct Fft {
@@ -191,9 +197,11 @@ struct Fft {
             const int k = i & (PP - 1);
             constexpr int OFF = (THREE && PP == R1) ? 0 : TW_MID;
             const cx<T>* __restrict__ tw = table + OFF + k;
+            constexpr bool FAST = ((L / R) % 16 == 0);
+            const cx<T>* sb = s + fft_pos(i);
             FCD_UNROLL
             for (int a = 0; a < R; ++a) {
-                cx<T> val = s[fft_pos(i + a * (L / R))];
+                cx<T> val = FAST ? sb[fft_padc(a * (L / R))] : s[fft_pos(i + a * (L / R))];
                 if (PP > 1 && a > 0) {
                     const cx<T> w = tw[a * PP];
                     val = val * (DIR < 0 ? w : conj(w));
@@ -213,9 +221,11 @@ struct Fft {
             const int k = i & (PP - 1);
             constexpr int OFF = (THREE && PP == R1) ? 0 : TW_MID;
             const cx<T>* __restrict__ tw = table + OFF + k;
+            constexpr bool FAST = ((L / R) % 16 == 0);
+            const int pb = fft_pos(i);
             FCD_UNROLL
             for (int a = 0; a < R; ++a) {
-                const int pos = fft_pos(i + a * (L / R));
+                const int pos = FAST ? pb + fft_padc(a * (L / R)) : fft_pos(i + a * (L / R));
                 cx<T> x0 = s0[pos], x1 = s1[pos];
                 if (PP > 1 && a > 0) {
                     cx<T> w = tw[a * PP];
@@ -243,8 +253,17 @@ struct Fft {
             const int i = t + TPF * ii;
             const int k = i & (PP - 1);
             const int j = (i - k) * R + k;
+            // j + a*PP never carries out of the low nibble in a way the constants below miss:
+            //   PP == 1 : j = i*R (R | 16), a < R            -> fft_pos(j) + a
+            //   PP == 8 : low nibble of j is k < 8            -> fft_pos(j) + 8a + (a >> 1)
+            //   PP % 16 == 0                                  -> fft_pos(j) + fft_padc(a*PP)
+            constexpr bool FAST = (PP == 1 && 16 % R == 0) || PP == 8 || (PP % 16 == 0);
+            cx<T>* sb = s + fft_pos(j);
             FCD_UNROLL
-            for (int a = 0; a < R; ++a) s[fft_pos(j + a * PP)] = v[ii + NB * a];
+            for (int a = 0; a < R; ++a) {
+                if (FAST) sb[PP == 1 ? a : (PP == 8 ? 8 * a + (a >> 1) : fft_padc(a * PP))] = v[ii + NB * a];
+                else s[fft_pos(j + a * PP)] = v[ii + NB * a];
+            }
         }
     }
 
