@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=2048)
     ap.add_argument("--frames", type=int, default=1000, help="frames per GPU per step (device-resident leg)")
-    ap.add_argument("--frames-per-launch", type=int, default=4)
+    ap.add_argument("--frames-per-launch", type=int, default=32)
     ap.add_argument("--e2e-frames", type=int, default=128, help="frames per step of the host-buffer leg")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=3, help="frames timed for the cpu_baseline object")

@@ -76,6 +76,16 @@ struct alignas(16) cf2 {
     cf a, b;
 };
 
+// w3 (row-transformed z = phi0 + i*phi1) is stored column-blocked so that the column kernel
+// reads one contiguous tile:  w3[f][slot/4][y][slot%4],  slot(kc) = kc for kc <= W/2 and
+// kc + 3 above (then the mirrored columns W-kc..W-kc-3 of a 4-column tile share one block).
+FCD_HD int w3_slot(int kc, int W) { return kc + (kc > W / 2 ? 3 : 0); }
+FCD_HD int w3_blocks(int W) { return W / 4 + 1; }
+FCD_HD long long w3_index(int f, int kc, int y, int H, int W) {
+    const int slot = w3_slot(kc, W);
+    return (((long long)f * w3_blocks(W) + (slot >> 2)) * H + y) * 4 + (slot & 3);
+}
+
 // Blocks are persistent: they copy the twiddle table of their transform length into shared
 // memory once (prologue) and then loop over tiles, so twiddle reads are LDS, not LDG.
 template <class F, int THREADS>
@@ -270,7 +280,7 @@ struct ColBand {
 struct RowDemodParams {
     const cf* w2;
     const float* theta;  // [2][H][W]  angle(ccsgn) of the bound reference
-    cf* w3;              // [F][H][W]
+    cf* w3;              // [F][W/4+1][H][4]  (column-blocked, see w3_index)
     float* colphase;     // [F][2][H]
     float* phases;       // [F][2][H][W] or null
     const cf* tw;
@@ -447,9 +457,8 @@ struct RowDemod {
             FF::stepC(st.v, t, s0);
         } else {
             FF::stepD(st.v, t, s0, tw);
-            cf* o = p.w3 + ((long long)f * p.H + y) * W;
             FCD_UNROLL
-            for (int m = 0; m < 16; ++m) o[t + TPF * m] = st.v[m];
+            for (int m = 0; m < 16; ++m) p.w3[w3_index(f, t + TPF * m, y, p.H, W)] = st.v[m];
         }
     }
 };
@@ -570,9 +579,9 @@ struct ColIntegrate {
 
     FCD_HD static void load_col(const Params& p, int f, int kc, int t, cf* v) {
         const int H = L;
-        const cf* base = p.w3 + (long long)f * H * p.W + kc;
+        const cf* base = p.w3 + w3_index(f, kc, t, H, p.W);
         FCD_UNROLL
-        for (int m = 0; m < 16; ++m) v[m] = base[(long long)(t + TPF * m) * p.W];
+        for (int m = 0; m < 16; ++m) v[m] = base[TPF * m * 4];
         if (kc == 0 && p.unwrap) {
             const float* r0 = p.rowoff + ((long long)f * 2 + 0) * H;
             const float* r1 = p.rowoff + ((long long)f * 2 + 1) * H;

@@ -352,7 +352,7 @@ struct PlanImpl {
         // workspaces
         w1.alloc((size_t)chunk * 2 * ncp * H);
         w2.alloc((size_t)chunk * 2 * ncp * H);
-        w3.alloc((size_t)chunk * n);
+        w3.alloc((size_t)chunk * w3_blocks(W) * H * 4);
         w4.alloc((size_t)chunk * H * w4p);
         colphase.alloc((size_t)chunk * 2 * H);
         rowoff.alloc((size_t)chunk * 2 * H);

@@ -112,7 +112,7 @@ class HeightMapPlan:
 
     Not thread-safe; use from one CUDA stream at a time (the current torch stream)."""
 
-    def __init__(self, shape: Sequence[int], frames_per_launch: int = 4, device=None):
+    def __init__(self, shape: Sequence[int], frames_per_launch: int = 16, device=None):
         _require_cuda()
         self.lib = load_library()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -297,7 +297,7 @@ class HeightMapPlan:
 _plan_cache: dict = {}
 
 
-def get_plan(shape, frames_per_launch: int = 4, device=None) -> HeightMapPlan:
+def get_plan(shape, frames_per_launch: int = 16, device=None) -> HeightMapPlan:
     _require_cuda()
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     key = (int(shape[0]), int(shape[1]), int(frames_per_launch), dev.index)
@@ -310,7 +310,7 @@ def get_plan(shape, frames_per_launch: int = 4, device=None) -> HeightMapPlan:
 
 def compute_height_maps(reference, frames, square_size, layers=None, height=None, unwrap=True,
                         return_phases=False, mask=None, plan: Optional[HeightMapPlan] = None,
-                        frames_per_launch: int = 4, out=None):
+                        frames_per_launch: int = 16, out=None):
     """Batched equivalent of calling fcd.compute_height_map(reference, frame, ...) for every
     frame (pydata/analyze.py:220-252) with the per-reference work done once.
 
