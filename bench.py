@@ -44,7 +44,8 @@ def parse_args():
     ap.add_argument("--size", type=int, default=2048)
     ap.add_argument("--frames", type=int, default=1000, help="frames per GPU per step (device-resident leg)")
     ap.add_argument("--frames-per-launch", type=int, default=32)
-    ap.add_argument("--e2e-frames", type=int, default=128, help="frames per step of the host-buffer leg")
+    ap.add_argument("--e2e-frames", type=int, default=256, help="frames per step of the host-buffer leg")
+    ap.add_argument("--e2e-chunk", type=int, default=8, help="frames per host<->device copy of the host-buffer leg")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=3, help="frames timed for the cpu_baseline object")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -278,7 +279,7 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         E = min(args.e2e_frames, F)
-        c = min(32, E)
+        c = min(args.e2e_chunk, E)
         h_in = torch.empty((E, n, n), dtype=torch.float32).pin_memory()
         h_in.copy_(frames[:E].cpu())
         h_out = torch.empty((E, n, n), dtype=torch.float32).pin_memory()
@@ -329,7 +330,7 @@ def run_ours(args):
         e2e = {"value": world * E * args.e2e_steps / float(tt.item()), "unit": "frames/s",
                "h2d_bytes_per_step": int(E * P * 4), "d2h_bytes_per_step": int(E * P * 4),
                "frames_per_step": E, "steps": args.e2e_steps,
-               "api": "fcd_b200.HeightMapPlan.execute on pinned host buffers, 32-frame chunks, copy/compute overlap"}
+               "api": f"fcd_b200.HeightMapPlan.execute on pinned host buffers, {c}-frame chunks, copy/compute overlap"}
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()

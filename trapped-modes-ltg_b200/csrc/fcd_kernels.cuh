@@ -300,7 +300,7 @@ struct RowDemod {
     using GL = GroupLayout<L, G, 2>;
     using Params = RowDemodParams;
     static constexpr bool BLOCKED_TILES = true;
-    static constexpr int MIN_BLOCKS = ((G * L / 16) <= 256 ? 2 : 1);
+    static constexpr int MIN_BLOCKS = ((G * L / 16) <= 128 ? 4 : ((G * L / 16) <= 256 ? 2 : 1));
     static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 12;
     using TW = SmemTwiddles<FF, THREADS>;
     // per group: two exchange buffers (one per carrier; the second doubles as the jump-scan
