@@ -53,6 +53,7 @@ struct GenRows : NoPrologue {
     using F = Fft<L, DIR, T>;
     using Params = GenRowsParams<T>;
     static constexpr bool BLOCKED_TILES = false;
+    static constexpr bool PIPELINED = false;
     static constexpr int MIN_BLOCKS = 1;
     static constexpr int TPF = L / 16, THREADS = G * TPF, PHASES = 4;
     static constexpr int STRIDE = L + L / 16;
@@ -107,6 +108,7 @@ struct GenCols : NoPrologue {
     using F = Fft<L, DIR, T>;
     using Params = GenColsParams<T>;
     static constexpr bool BLOCKED_TILES = false;
+    static constexpr bool PIPELINED = false;
     static constexpr int MIN_BLOCKS = 1;
     static constexpr int TPF = L / 16, THREADS = G * TPF, PHASES = 4;
     static constexpr int STRIDE = L + L / 16;
@@ -149,6 +151,7 @@ struct SumParams {
 struct SumKernel : NoPrologue {
     using Params = SumParams;
     static constexpr bool BLOCKED_TILES = false;
+    static constexpr bool PIPELINED = false;
     static constexpr int MIN_BLOCKS = 1;
     static constexpr int THREADS = 256, PHASES = 2, SMEM_BYTES = THREADS * (int)sizeof(double);
     struct State { int dummy; };
@@ -185,6 +188,7 @@ struct SpecMagParams {
 struct SpecMag : NoPrologue {
     using Params = SpecMagParams;
     static constexpr bool BLOCKED_TILES = false;
+    static constexpr bool PIPELINED = false;
     static constexpr int MIN_BLOCKS = 1;
     static constexpr int THREADS = 256, PHASES = 1, SMEM_BYTES = 16;
     struct State { int dummy; };
@@ -218,6 +222,7 @@ struct CandidatesParams {
 struct Candidates : NoPrologue {
     using Params = CandidatesParams;
     static constexpr bool BLOCKED_TILES = false;
+    static constexpr bool PIPELINED = false;
     static constexpr int MIN_BLOCKS = 1;
     static constexpr int THREADS = 256, PHASES = 1, SMEM_BYTES = 16;
     struct State { int dummy; };
@@ -249,6 +254,7 @@ struct MaskMulParams {
 struct MaskMul : NoPrologue {
     using Params = MaskMulParams;
     static constexpr bool BLOCKED_TILES = false;
+    static constexpr bool PIPELINED = false;
     static constexpr int MIN_BLOCKS = 1;
     static constexpr int THREADS = 256, PHASES = 1, SMEM_BYTES = 16;
     struct State { int dummy; };
@@ -279,6 +285,7 @@ struct CcsgnStoreParams {
 struct CcsgnStore : NoPrologue {
     using Params = CcsgnStoreParams;
     static constexpr bool BLOCKED_TILES = false;
+    static constexpr bool PIPELINED = false;
     static constexpr int MIN_BLOCKS = 1;
     static constexpr int THREADS = 256, PHASES = 1, SMEM_BYTES = 16;
     struct State { int dummy; };

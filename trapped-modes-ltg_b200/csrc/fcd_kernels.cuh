@@ -97,6 +97,26 @@ struct SmemTwiddles {
         for (int i = tid; i < F::TW_ELEMS; i += THREADS) s[i] = g[i];
     }
 };
+// asynchronous 8-byte global -> shared copy (LDGSTS); the CPU emulation copies immediately
+FCD_HD void async_copy8(void* smem_dst, const void* gsrc) {
+#if defined(__CUDA_ARCH__)
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+#else
+    *reinterpret_cast<cf*>(smem_dst) = *reinterpret_cast<const cf*>(gsrc);
+#endif
+}
+FCD_HD void async_wait_all() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+// state the launcher maintains for kernels that prefetch the next tile (K::PIPELINED)
+struct TileLink {
+    int next_bx, next_by;
+    bool has_next, first;
+};
+
 struct NoPrologue {
     template <class P> FCD_HD static void prologue(const P&, int, unsigned char*) {}
 };
@@ -123,7 +143,8 @@ struct RowFwd {
     using GL = GroupLayout<L, G>;
     using Params = RowFwdParams;
     static constexpr bool BLOCKED_TILES = false;
-    static constexpr int MIN_BLOCKS = ((G * L / 16) <= 256 ? 3 : 1);
+    static constexpr bool PIPELINED = false;
+    static constexpr int MIN_BLOCKS = ((G * L / 16) <= 128 ? 6 : ((G * L / 16) <= 256 ? 3 : 1));
     static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 6;
     using TW = SmemTwiddles<F, THREADS>;
     static constexpr int SMEM_BYTES = TW::TW_BYTES + G * GL::STRIDE * (int)sizeof(cf);
@@ -213,6 +234,7 @@ struct ColBand {
     using GL = GroupLayout<L, G>;
     using Params = ColBandParams;
     static constexpr bool BLOCKED_TILES = false;
+    static constexpr bool PIPELINED = false;
     static constexpr int MIN_BLOCKS = ((G * L / 16) <= 256 ? 2 : 1);
     static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 8;
     using TW = SmemTwiddles<FF, THREADS>;
@@ -300,6 +322,7 @@ struct RowDemod {
     using GL = GroupLayout<L, G, 2>;
     using Params = RowDemodParams;
     static constexpr bool BLOCKED_TILES = true;
+    static constexpr bool PIPELINED = false;
     static constexpr int MIN_BLOCKS = ((G * L / 16) <= 128 ? 4 : ((G * L / 16) <= 256 ? 2 : 1));
     static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 12;
     using TW = SmemTwiddles<FF, THREADS>;
@@ -478,6 +501,7 @@ struct RowLinkParams {
 struct RowLink : NoPrologue {
     using Params = RowLinkParams;
     static constexpr bool BLOCKED_TILES = false;
+    static constexpr bool PIPELINED = false;
     static constexpr int MIN_BLOCKS = 1;
     static constexpr int THREADS = 256, PHASES = 4;
     static constexpr int MAXH = 4096;
@@ -529,6 +553,7 @@ struct PhaseFixParams {
 struct PhaseFix : NoPrologue {
     using Params = PhaseFixParams;
     static constexpr bool BLOCKED_TILES = false;
+    static constexpr bool PIPELINED = false;
     static constexpr int MIN_BLOCKS = 1;
     static constexpr int THREADS = 256, PHASES = 1, SMEM_BYTES = 16;
     struct State { int dummy; };
@@ -570,75 +595,87 @@ struct ColIntegrate {
     using GL = GroupLayout<L, G, 2>;
     using Params = ColIntegrateParams;
     static constexpr bool BLOCKED_TILES = false;
+    static constexpr bool PIPELINED = true;
     static constexpr int MIN_BLOCKS = 1;
     static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 9;
     using TW = SmemTwiddles<FF, THREADS>;
     static constexpr int SMEM_BYTES = TW::TW_BYTES + G * GL::GROUP_STRIDE * (int)sizeof(cf);
     FCD_HD static void prologue(const Params& p, int tid, unsigned char* smem) { TW::load(p.tw, tid, smem); }
-    struct State { cf v[16]; cf va[16]; };
+    struct State { cf v[16]; cf va[16]; TileLink link; };
 
-    FCD_HD static void load_col(const Params& p, int f, int kc, int t, cf* v) {
-        const int H = L;
-        const cf* base = p.w3 + w3_index(f, kc, t, H, p.W);
-        FCD_UNROLL
-        for (int m = 0; m < 16; ++m) v[m] = base[TPF * m * 4];
-        if (kc == 0 && p.unwrap) {
-            const float* r0 = p.rowoff + ((long long)f * 2 + 0) * H;
-            const float* r1 = p.rowoff + ((long long)f * 2 + 1) * H;
-            const float w = (float)p.W;
-            FCD_UNROLL
-            for (int m = 0; m < 16; ++m) {
-                v[m].x += w * r0[t + TPF * m];
-                v[m].y += w * r1[t + TPF * m];
-            }
-        }
-    }
+    FCD_HD static const cf* col_ptr(const Params& p, int f, int kc, int t) { return p.w3 + w3_index(f, kc, t, L, p.W); }
 
-    // Both columns of a conjugate pair (kc, W-kc) are transformed together: one exposure of the
-    // global-load latency per tile and every twiddle is loaded once for the two transforms.
+    // Column pair (kc, W-kc) of z_row = Phi0_row + i Phi1_row.  The two real fields' row spectra
+    // are separated pointwise (Hermitian symmetry in kc) *before* the column transforms, so
+    // the transforms of Phi0 and Phi1 are combined locally afterwards.  While the inverse
+    // transform runs, the next tile's columns are prefetched: column kc into the idle
+    // registers, column W-kc with cp.async into the idle exchange buffer.
     template <int PH>
     FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem_all, State& st) {
         const cf* tw = reinterpret_cast<const cf*>(smem_all);
         unsigned char* smem = smem_all + TW::TW_BYTES;
         const int g = tid % G, t = tid / G;   // group fastest: a warp covers 32/G rows x G columns
-        cf* s0 = reinterpret_cast<cf*>(smem) + g * GL::GROUP_STRIDE;   // column kc, later the inverse
-        cf* s1 = s0 + GL::STRIDE;                                        // column W-kc
+        cf* s0 = reinterpret_cast<cf*>(smem) + g * GL::GROUP_STRIDE;
+        cf* s1 = s0 + GL::STRIDE;
         const int H = L;
         const int f = by;
         const int kc = bx * G + g;
         const bool valid = kc <= p.W / 2;
         const int kcm = (p.W - kc) & (p.W - 1);
         if constexpr (PH == 0) {
+            if (st.link.first) {
+                if (valid) {
+                    const cf* a = col_ptr(p, f, kc, t);
+                    const cf* b = col_ptr(p, f, kcm, t);
+                    FCD_UNROLL
+                    for (int m = 0; m < 16; ++m) st.va[m] = a[TPF * m * 4];
+                    FCD_UNROLL
+                    for (int m = 0; m < 16; ++m) st.v[m] = b[TPF * m * 4];
+                }
+            } else {
+                async_wait_all();   // each thread reads back only what it copied itself
+                FCD_UNROLL
+                for (int m = 0; m < 16; ++m) st.v[m] = s1[fft_nat<TPF>(t, m)];
+            }
+        } else if constexpr (PH == 1) {
             if (valid) {
-                load_col(p, f, kc, t, st.va);
-                load_col(p, f, kcm, t, st.v);
+                if (kc == 0 && p.unwrap) {   // row offsets of the unwrap enter only the kc = 0 column
+                    const float* r0 = p.rowoff + ((long long)f * 2 + 0) * H;
+                    const float* r1 = p.rowoff + ((long long)f * 2 + 1) * H;
+                    const float w = (float)p.W;
+                    FCD_UNROLL
+                    for (int m = 0; m < 16; ++m) {
+                        const cf add = mk<float>(w * r0[t + TPF * m], w * r1[t + TPF * m]);
+                        st.va[m] = st.va[m] + add;
+                        st.v[m] = st.v[m] + add;      // kcm == kc == 0
+                    }
+                }
+                FCD_UNROLL
+                for (int m = 0; m < 16; ++m) {
+                    const cf z = st.va[m], zm = conj(st.v[m]);
+                    st.va[m] = z + zm;              // 2 * Phi0_row(y, kc)
+                    st.v[m] = mul_mi(z - zm);       // 2 * Phi1_row(y, kc)
+                }
             } else {
                 FCD_UNROLL
                 for (int m = 0; m < 16; ++m) { st.va[m] = mk<float>(0.f, 0.f); st.v[m] = mk<float>(0.f, 0.f); }
             }
             FF::stepA(st.va, t, s0);
             FF::stepA(st.v, t, s1);
-        } else if constexpr (PH == 1) {
-            FF::stepB2(st.va, st.v, t, s0, s1, tw);
         } else if constexpr (PH == 2) {
+            FF::stepB2(st.va, st.v, t, s0, s1, tw);
+        } else if constexpr (PH == 3) {
             FF::stepC(st.va, t, s0);
             FF::stepC(st.v, t, s1);
-        } else if constexpr (PH == 3) {
-            FF::stepD2(st.va, st.v, t, s0, s1, tw);
         } else if constexpr (PH == 4) {
-            FCD_UNROLL
-            for (int m = 0; m < 16; ++m) s1[fft_nat<TPF>(t, m)] = st.v[m];   // Z(., W-kc), natural order
-        } else if constexpr (PH == 5) {
+            FF::stepD2(st.va, st.v, t, s0, s1, tw);
             if (valid) {
                 const float kxv = p.kx[kc], kxa = p.kxq[kc], kxb = p.kxq[kcm];
                 FCD_UNROLL
                 for (int m = 0; m < 16; ++m) {
                     const int kr = t + TPF * m;
-                    const int krm = (H - kr) & (H - 1);
-                    const cf zm = conj(s1[fft_pos(krm)]);      // conj Z(-kr, -kc)
-                    const cf z = st.va[m];                      // Z(kr, kc)
-                    const cf p0 = z + zm;                       // 2 * Phi0(k)
-                    const cf p1 = mul_mi(z - zm);               // 2 * Phi1(k)
+                    const cf p0 = st.va[m];                     // 2 * Phi0(k)
+                    const cf p1 = st.v[m];                      // 2 * Phi1(k)
                     const float kyv = (float)(kr < H / 2 ? kr : kr - H) * p.dky;          // ky[kr]
                     const float kya = (kr == H / 2 + 1) ? 0.f : kyv;                     // quirk-zeroed ky[kr]
                     const float kym = (kr == H / 2) ? kyv : -kyv;                        // ky[-kr]
@@ -658,7 +695,20 @@ struct ColIntegrate {
                 FCD_UNROLL
                 for (int m = 0; m < 16; ++m) st.v[m] = mk<float>(0.f, 0.f);
             }
+        } else if constexpr (PH == 5) {
             FI::stepA(st.v, t, s0);
+            if (st.link.has_next) {       // prefetch the next tile (both buffers' readers are past the barrier)
+                const int nkc = st.link.next_bx * G + g, nf = st.link.next_by;
+                if (nkc <= p.W / 2) {
+                    const int nkcm = (p.W - nkc) & (p.W - 1);
+                    const cf* a = col_ptr(p, nf, nkc, t);
+                    const cf* b = col_ptr(p, nf, nkcm, t);
+                    FCD_UNROLL
+                    for (int m = 0; m < 16; ++m) st.va[m] = a[TPF * m * 4];
+                    FCD_UNROLL
+                    for (int m = 0; m < 16; ++m) async_copy8(&s1[fft_nat<TPF>(t, m)], &b[TPF * m * 4]);
+                }
+            }
         } else if constexpr (PH == 6) {
             FI::stepB(st.v, t, s0, tw);
         } else if constexpr (PH == 7) {
@@ -673,6 +723,7 @@ struct ColIntegrate {
         }
     }
 };
+
 
 
 // =========================================================================================
@@ -693,7 +744,8 @@ struct RowInv {
     using GL = GroupLayout<L, G>;
     using Params = RowInvParams;
     static constexpr bool BLOCKED_TILES = false;
-    static constexpr int MIN_BLOCKS = ((G * L / 16) <= 256 ? 3 : 1);
+    static constexpr bool PIPELINED = false;
+    static constexpr int MIN_BLOCKS = ((G * L / 16) <= 128 ? 6 : ((G * L / 16) <= 256 ? 3 : 1));
     static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 4;
     using TW = SmemTwiddles<FI, THREADS>;
     static constexpr int SMEM_BYTES = TW::TW_BYTES + G * GL::STRIDE * (int)sizeof(cf);

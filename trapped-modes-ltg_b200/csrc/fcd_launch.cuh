@@ -52,11 +52,19 @@ inline void launch(int gx, int gy, stream_t, const typename K::Params& p) {
         std::vector<unsigned char> smem((size_t)K::SMEM_BYTES + 16, 0xCD);
         std::vector<typename K::State> st(K::THREADS);
         for (int tid = 0; tid < K::THREADS; ++tid) K::prologue(p, tid, smem.data());
+        int t0 = b, t1 = ntiles, step = grid;
         if (K::BLOCKED_TILES) {
-            const int t0 = (int)((long long)b * ntiles / grid), t1 = (int)((long long)(b + 1) * ntiles / grid);
-            for (int tile = t0; tile < t1; ++tile) emu_phases<K, 0>(p, tile % gx, tile / gx, smem.data(), st.data());
-        } else {
-            for (int tile = b; tile < ntiles; tile += grid) emu_phases<K, 0>(p, tile % gx, tile / gx, smem.data(), st.data());
+            t0 = (int)((long long)b * ntiles / grid);
+            t1 = (int)((long long)(b + 1) * ntiles / grid);
+            step = 1;
+        }
+        for (int tile = t0; tile < t1; tile += step) {
+            if constexpr (K::PIPELINED) {
+                const int nt = tile + step;
+                for (int tid = 0; tid < K::THREADS; ++tid)
+                    st[tid].link = TileLink{nt % gx, nt / gx, nt < t1, tile == t0};
+            }
+            emu_phases<K, 0>(p, tile % gx, tile / gx, smem.data(), st.data());
         }
     }
 }
@@ -104,21 +112,22 @@ __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) fcd_kernel(const __
     typename K::State st;
     K::prologue(p, (int)threadIdx.x, fcd_smem);
     __syncthreads();
+    // BLOCKED_TILES: contiguous tile range per block (bx fastest), a block's consecutive tiles
+    // share inputs.  Otherwise round robin: tiles that share 128-byte lines (adjacent column /
+    // row tiles) run at the same time on neighbouring blocks, so partial lines merge in L2.
+    int t0 = blockIdx.x, t1 = ntiles, step = gridDim.x;
     if (K::BLOCKED_TILES) {
-        // contiguous tile range per block (bx fastest): a block's consecutive tiles share inputs
-        const int t0 = (int)((long long)blockIdx.x * ntiles / gridDim.x);
-        const int t1 = (int)((long long)(blockIdx.x + 1) * ntiles / gridDim.x);
-        for (int tile = t0; tile < t1; ++tile) {
-            run_phases<K, 0>(p, tile % gx, tile / gx, fcd_smem, st);
-            __syncthreads();
+        t0 = (int)((long long)blockIdx.x * ntiles / gridDim.x);
+        t1 = (int)((long long)(blockIdx.x + 1) * ntiles / gridDim.x);
+        step = 1;
+    }
+    for (int tile = t0; tile < t1; tile += step) {
+        if constexpr (K::PIPELINED) {
+            const int nt = tile + step;
+            st.link = TileLink{nt % gx, nt / gx, nt < t1, tile == t0};
         }
-    } else {
-        // round robin: tiles that share 128-byte lines (adjacent column / row tiles) run at the
-        // same time on neighbouring blocks, so partial-line traffic merges in L2
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            run_phases<K, 0>(p, tile % gx, tile / gx, fcd_smem, st);
-            __syncthreads();
-        }
+        run_phases<K, 0>(p, tile % gx, tile / gx, fcd_smem, st);
+        __syncthreads();
     }
 }
 

@@ -21,7 +21,16 @@ template <> struct Tune<128>  { static constexpr int GROW = 8,  GCOL = 8,  GDEM 
 template <> struct Tune<256>  { static constexpr int GROW = 8,  GCOL = 8,  GDEM = 8,  GGEN = 8; };
 template <> struct Tune<512>  { static constexpr int GROW = 4,  GCOL = 4,  GDEM = 4,  GGEN = 4; };
 template <> struct Tune<1024> { static constexpr int GROW = 4,  GCOL = 4,  GDEM = 4,  GGEN = 4; };
-template <> struct Tune<2048> { static constexpr int GROW = 2,  GCOL = 4,  GDEM = 2,  GGEN = 2; };
+#ifndef FCD_T2048_GROW
+#define FCD_T2048_GROW 2
+#endif
+#ifndef FCD_T2048_GCOL
+#define FCD_T2048_GCOL 4
+#endif
+#ifndef FCD_T2048_GDEM
+#define FCD_T2048_GDEM 2
+#endif
+template <> struct Tune<2048> { static constexpr int GROW = FCD_T2048_GROW, GCOL = FCD_T2048_GCOL, GDEM = FCD_T2048_GDEM, GGEN = 2; };
 template <> struct Tune<4096> { static constexpr int GROW = 2,  GCOL = 2,  GDEM = 2,  GGEN = 2; };
 
 #define FCD_CASE_L(N, ...) case N: { constexpr int L = N; __VA_ARGS__; } break;

@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG_DIR, "libfcd_b200.so")
+LIB_PATH = os.environ.get("FCD_B200_LIB", os.path.join(_PKG_DIR, "libfcd_b200.so"))
 
 FCD_OK, FCD_ERR_INVALID, FCD_ERR_RUNTIME, FCD_ERR_STATE, FCD_ERR_NOPEAKS = 0, -1, -2, -3, -4
 
