@@ -54,6 +54,7 @@ struct GenRows : NoPrologue {
     using Params = GenRowsParams<T>;
     static constexpr bool BLOCKED_TILES = false;
     static constexpr bool PIPELINED = false;
+    static constexpr int SYNC_THREADS = 0;   // 0: block-wide barrier
     static constexpr int MIN_BLOCKS = 1;
     static constexpr int TPF = L / 16, THREADS = G * TPF, PHASES = 4;
     static constexpr int STRIDE = L + L / 16;
@@ -109,6 +110,7 @@ struct GenCols : NoPrologue {
     using Params = GenColsParams<T>;
     static constexpr bool BLOCKED_TILES = false;
     static constexpr bool PIPELINED = false;
+    static constexpr int SYNC_THREADS = 0;   // 0: block-wide barrier
     static constexpr int MIN_BLOCKS = 1;
     static constexpr int TPF = L / 16, THREADS = G * TPF, PHASES = 4;
     static constexpr int STRIDE = L + L / 16;
@@ -152,6 +154,7 @@ struct SumKernel : NoPrologue {
     using Params = SumParams;
     static constexpr bool BLOCKED_TILES = false;
     static constexpr bool PIPELINED = false;
+    static constexpr int SYNC_THREADS = 0;   // 0: block-wide barrier
     static constexpr int MIN_BLOCKS = 1;
     static constexpr int THREADS = 256, PHASES = 2, SMEM_BYTES = THREADS * (int)sizeof(double);
     struct State { int dummy; };
@@ -189,6 +192,7 @@ struct SpecMag : NoPrologue {
     using Params = SpecMagParams;
     static constexpr bool BLOCKED_TILES = false;
     static constexpr bool PIPELINED = false;
+    static constexpr int SYNC_THREADS = 0;   // 0: block-wide barrier
     static constexpr int MIN_BLOCKS = 1;
     static constexpr int THREADS = 256, PHASES = 1, SMEM_BYTES = 16;
     struct State { int dummy; };
@@ -223,6 +227,7 @@ struct Candidates : NoPrologue {
     using Params = CandidatesParams;
     static constexpr bool BLOCKED_TILES = false;
     static constexpr bool PIPELINED = false;
+    static constexpr int SYNC_THREADS = 0;   // 0: block-wide barrier
     static constexpr int MIN_BLOCKS = 1;
     static constexpr int THREADS = 256, PHASES = 1, SMEM_BYTES = 16;
     struct State { int dummy; };
@@ -255,6 +260,7 @@ struct MaskMul : NoPrologue {
     using Params = MaskMulParams;
     static constexpr bool BLOCKED_TILES = false;
     static constexpr bool PIPELINED = false;
+    static constexpr int SYNC_THREADS = 0;   // 0: block-wide barrier
     static constexpr int MIN_BLOCKS = 1;
     static constexpr int THREADS = 256, PHASES = 1, SMEM_BYTES = 16;
     struct State { int dummy; };
@@ -286,6 +292,7 @@ struct CcsgnStore : NoPrologue {
     using Params = CcsgnStoreParams;
     static constexpr bool BLOCKED_TILES = false;
     static constexpr bool PIPELINED = false;
+    static constexpr int SYNC_THREADS = 0;   // 0: block-wide barrier
     static constexpr int MIN_BLOCKS = 1;
     static constexpr int THREADS = 256, PHASES = 1, SMEM_BYTES = 16;
     struct State { int dummy; };

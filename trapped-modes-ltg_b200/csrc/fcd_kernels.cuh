@@ -144,6 +144,7 @@ struct RowFwd {
     using Params = RowFwdParams;
     static constexpr bool BLOCKED_TILES = false;
     static constexpr bool PIPELINED = false;
+    static constexpr int SYNC_THREADS = 0;   // 0: block-wide barrier
     static constexpr int MIN_BLOCKS = ((G * L / 16) <= 128 ? 6 : ((G * L / 16) <= 256 ? 3 : 1));
     static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 6;
     using TW = SmemTwiddles<F, THREADS>;
@@ -235,6 +236,7 @@ struct ColBand {
     using Params = ColBandParams;
     static constexpr bool BLOCKED_TILES = false;
     static constexpr bool PIPELINED = false;
+    static constexpr int SYNC_THREADS = 0;   // 0: block-wide barrier
     static constexpr int MIN_BLOCKS = ((G * L / 16) <= 256 ? 2 : 1);
     static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 8;
     using TW = SmemTwiddles<FF, THREADS>;
@@ -323,6 +325,7 @@ struct RowDemod {
     using Params = RowDemodParams;
     static constexpr bool BLOCKED_TILES = true;
     static constexpr bool PIPELINED = false;
+    static constexpr int SYNC_THREADS = (L / 16 >= 32 && G > 1 && G <= 15) ? L / 16 : 0;   // per-group named barriers
     static constexpr int MIN_BLOCKS = ((G * L / 16) <= 128 ? 4 : ((G * L / 16) <= 256 ? 2 : 1));
     static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 12;
     using TW = SmemTwiddles<FF, THREADS>;
@@ -502,6 +505,7 @@ struct RowLink : NoPrologue {
     using Params = RowLinkParams;
     static constexpr bool BLOCKED_TILES = false;
     static constexpr bool PIPELINED = false;
+    static constexpr int SYNC_THREADS = 0;   // 0: block-wide barrier
     static constexpr int MIN_BLOCKS = 1;
     static constexpr int THREADS = 256, PHASES = 4;
     static constexpr int MAXH = 4096;
@@ -554,6 +558,7 @@ struct PhaseFix : NoPrologue {
     using Params = PhaseFixParams;
     static constexpr bool BLOCKED_TILES = false;
     static constexpr bool PIPELINED = false;
+    static constexpr int SYNC_THREADS = 0;   // 0: block-wide barrier
     static constexpr int MIN_BLOCKS = 1;
     static constexpr int THREADS = 256, PHASES = 1, SMEM_BYTES = 16;
     struct State { int dummy; };
@@ -596,6 +601,7 @@ struct ColIntegrate {
     using Params = ColIntegrateParams;
     static constexpr bool BLOCKED_TILES = false;
     static constexpr bool PIPELINED = true;
+    static constexpr int SYNC_THREADS = 0;   // 0: block-wide barrier
     static constexpr int MIN_BLOCKS = 1;
     static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 9;
     using TW = SmemTwiddles<FF, THREADS>;
@@ -745,6 +751,7 @@ struct RowInv {
     using Params = RowInvParams;
     static constexpr bool BLOCKED_TILES = false;
     static constexpr bool PIPELINED = false;
+    static constexpr int SYNC_THREADS = (L / 16 >= 32 && G > 1 && G <= 15) ? L / 16 : 0;   // per-group named barriers
     static constexpr int MIN_BLOCKS = ((G * L / 16) <= 128 ? 6 : ((G * L / 16) <= 256 ? 3 : 1));
     static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 4;
     using TW = SmemTwiddles<FI, THREADS>;

@@ -94,12 +94,26 @@ inline void d2d(void* d, const void* s_, size_t n, stream_t s) {
 }
 inline void sync(stream_t s) { check(cudaStreamSynchronize((cudaStream_t)s), "cudaStreamSynchronize"); }
 
+// Barrier between phases.  Kernels whose groups (one transform each, contiguous warps) never
+// exchange data use a named barrier per group, so the groups of a block drift apart and
+// overlap each other's load / compute / store phases instead of marching in lockstep.
+template <class K>
+__device__ __forceinline__ void phase_barrier() {
+    if constexpr (K::SYNC_THREADS == 0) {
+        __syncthreads();
+    } else {
+        static_assert(K::SYNC_THREADS % 32 == 0 && K::THREADS / K::SYNC_THREADS <= 15, "named barrier per group");
+        const int id = 1 + (int)threadIdx.x / K::SYNC_THREADS;
+        asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(K::SYNC_THREADS) : "memory");
+    }
+}
+
 template <class K, int PH>
 __device__ __forceinline__ void run_phases(const typename K::Params& p, int bx, int by, unsigned char* smem,
                                            typename K::State& st) {
     K::template phase<PH>(p, bx, by, (int)threadIdx.x, smem, st);
     if constexpr (PH + 1 < K::PHASES) {
-        __syncthreads();
+        phase_barrier<K>();
         run_phases<K, PH + 1>(p, bx, by, smem, st);
     }
 }
@@ -127,7 +141,7 @@ __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) fcd_kernel(const __
             st.link = TileLink{nt % gx, nt / gx, nt < t1, tile == t0};
         }
         run_phases<K, 0>(p, tile % gx, tile / gx, fcd_smem, st);
-        __syncthreads();
+        phase_barrier<K>();
     }
 }
 
