@@ -36,7 +36,7 @@ FCD_HD float fast_div(float a, float b) {
 #endif
 }
 
-// Branch-free atan2 (max abs error 3e-7 rad, i.e. about one ulp of pi in float32).  The
+// Branch-free atan2 (degree-7 minimax in a^2; max abs error 3e-7 rad, about one ulp of pi in float32).  The
 // library atan2f compiles to calls and divergent slow paths, which stops the compiler from
 // batching the loads around it (ncu profiles/r01: one exposed DRAM round trip per element).
 // np.angle(0) = 0 is preserved.
@@ -45,15 +45,14 @@ FCD_HD float fast_atan2f(float y, float x) {
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
     const float a = fast_div(mn, mx);
     const float s = a * a;
-    float r = 0.002456723479554057f;
-    r = r * s + -0.01440135296434164f;
-    r = r * s + 0.03978121653199196f;
-    r = r * s + -0.07234856486320496f;
-    r = r * s + 0.10498945415019989f;
-    r = r * s + -0.14161229133605957f;
-    r = r * s + 0.19985906779766083f;
-    r = r * s + -0.33332598209381104f;
-    r = r * s + 0.9999998807907104f;
+    float r = -0.004054565913975239f;
+    r = r * s + 0.021862953901290894f;
+    r = r * s + -0.0559123195707798f;
+    r = r * s + 0.0964219719171524f;
+    r = r * s + -0.1390862911939621f;
+    r = r * s + 0.19946566224098206f;
+    r = r * s + -0.33329859375953674f;
+    r = r * s + 0.9999993443489075f;
     r = r * a;
     r = (ay > ax) ? 1.57079632679489661923f - r : r;
     r = (x < 0.f) ? 3.14159265358979323846f - r : r;
@@ -117,7 +116,12 @@ struct TileLink {
     bool has_next, first;
 };
 
-struct NoPrologue {
+// phases may be skipped (together with their trailing barrier) when a kernel says so; the
+// answer must be uniform over the barrier domain (block, or group for named barriers)
+struct AllPhases {
+    template <int PH, class P> FCD_HD static bool enabled(const P&, const unsigned char*, int) { return true; }
+};
+struct NoPrologue : AllPhases {
     template <class P> FCD_HD static void prologue(const P&, int, unsigned char*) {}
 };
 
@@ -138,7 +142,7 @@ struct RowFwdParams {
 };
 
 template <int L, int G>
-struct RowFwd {
+struct RowFwd : AllPhases {
     using F = Fft<L, -1, float>;
     using GL = GroupLayout<L, G>;
     using Params = RowFwdParams;
@@ -229,7 +233,7 @@ struct ColBandParams {
 };
 
 template <int L, int G>
-struct ColBand {
+struct ColBand : AllPhases {
     using FF = Fft<L, -1, float>;
     using FI = Fft<L, +1, float>;
     using GL = GroupLayout<L, G>;
@@ -327,7 +331,7 @@ struct RowDemod {
     static constexpr bool PIPELINED = false;
     static constexpr int SYNC_THREADS = (L / 16 >= 32 && G > 1 && G <= 15) ? L / 16 : 0;   // per-group named barriers
     static constexpr int MIN_BLOCKS = ((G * L / 16) <= 128 ? 4 : ((G * L / 16) <= 256 ? 2 : 1));
-    static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 12;
+    static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 13;
     using TW = SmemTwiddles<FF, THREADS>;
     // per group: two exchange buffers (one per carrier; the second doubles as the jump-scan
     // array), chunk totals, chunk offsets, flag
@@ -337,32 +341,50 @@ struct RowDemod {
     FCD_HD static void prologue(const Params& p, int tid, unsigned char* smem) { TW::load(p.tw, tid, smem); }
     struct State {
         cf v[16];   // carrier 0, later (phi0, phi1)
-        cf w[16];   // carrier 1, later the row jumps
+        cf w[16];   // carrier 1
     };
+
+    FCD_HD static int* group_flag(unsigned char* smem_all, int tid) {
+        unsigned char* gbase = smem_all + TW::TW_BYTES + (size_t)(tid / TPF) * GROUP_BYTES;
+        return reinterpret_cast<int*>(gbase + GL::GROUP_STRIDE * sizeof(cf)) + 4 * TPF;
+    }
+    // Phases 4..8 are the row unwrap.  A 2*pi jump between neighbours needs |phi| > pi/2
+    // somewhere in the row, which phase 3 detects thread-locally; rows that cannot wrap skip
+    // the whole block (group-uniform: the flag is per row).
+    template <int PH>
+    FCD_HD static bool enabled(const Params& p, const unsigned char* smem_all, int tid) {
+        if constexpr (PH >= 4 && PH <= 8)
+            return p.unwrap && *group_flag(const_cast<unsigned char*>(smem_all), tid) != 0;
+        else
+            return true;
+    }
 
     FCD_HD static void load_band(const Params& p, int f, int i, int y, int t, cf* v) {
         const int W = L;
-        const cf* row = p.w2 + (((long long)f * 2 + i) * p.H + y) * p.ncp;
+        const cf* __restrict__ row = p.w2 + (((long long)f * 2 + i) * p.H + y) * p.ncp;
+        const int c0 = (t - p.kc0[i]) & (W - 1);     // band column of spectrum position t
+        const int nc = p.nc[i];
         FCD_UNROLL
         for (int m = 0; m < 16; ++m) {
-            const int pidx = t + TPF * m;
-            const int kc = pidx < W / 2 ? pidx : pidx - W;
-            const int c = kc - p.kc0[i];
-            v[m] = (c >= 0 && c < p.nc[i]) ? row[c] : mk<float>(0.f, 0.f);
+            const int c = (c0 + TPF * m) & (W - 1);
+            v[m] = (c < nc) ? row[c] : mk<float>(0.f, 0.f);
         }
     }
     // -angle(g * ccsgn) = -wrap(angle(g) + angle(ccsgn))           (fcd.py:118)
-    FCD_HD static void demod(const Params& p, int i, int y, int t, const cf* v, float* ph) {
+    FCD_HD static bool demod(const Params& p, int i, int y, int t, const cf* v, float* ph) {
         const int W = L;
         const float* __restrict__ th = p.theta + ((long long)i * p.H + y) * W;
         float c[16];
         FCD_UNROLL
         for (int m = 0; m < 16; ++m) c[m] = th[t + TPF * m];     // all loads in flight first
+        float big = 0.f;
         FCD_UNROLL
         for (int m = 0; m < 16; ++m) {
             const float a = fast_atan2f(v[m].y, v[m].x) + c[m];
             ph[m] = kTwoPiF * rintf(a * kInvTwoPiF) - a;
+            big = fmaxf(big, fabsf(ph[m]));
         }
+        return big > 1.57079632679489661923f;
     }
 
     // Both carriers of a row are transformed together (shared twiddle loads, half the barriers).
@@ -396,8 +418,9 @@ struct RowDemod {
         } else if constexpr (PH == 3) {
             FI::stepD2(st.v, st.w, t, s0, s1, tw);
             float ph0[16], ph1[16];
-            demod(p, 0, y, t, st.v, ph0);
-            demod(p, 1, y, t, st.w, ph1);
+            const bool big0 = demod(p, 0, y, t, st.v, ph0);
+            const bool big1 = demod(p, 1, y, t, st.w, ph1);
+            if (big0 || big1) *flag = 1;      // this row may contain 2*pi jumps
             FCD_UNROLL
             for (int m = 0; m < 16; ++m) st.v[m] = mk<float>(ph0[m], ph1[m]);
             // wrapped phase at the anchor column links the rows (RowLink)
@@ -411,62 +434,50 @@ struct RowDemod {
                 p.colphase[((long long)f * 2 + 1) * p.H + y] = a.y;
             }
         } else if constexpr (PH == 4) {
-            if (p.unwrap) {
-                FCD_UNROLL
-                for (int m = 0; m < 16; ++m) s0[fft_nat<TPF>(t, m)] = st.v[m];
-            }
+            FCD_UNROLL
+            for (int m = 0; m < 16; ++m) s0[fft_nat<TPF>(t, m)] = st.v[m];
         } else if constexpr (PH == 5) {
             // 2*pi jumps to the left neighbour -> buffer 1 (as integers)
-            if (p.unwrap) {
-                bool any = false;
-                FCD_UNROLL
-                for (int m = 0; m < 16; ++m) {
-                    const int x = t + TPF * m;
-                    int2s j; j.a = 0; j.b = 0;
-                    if (x > 0) {
-                        const cf prev = s0[fft_pos(x - 1)];
-                        j.a = (int)rintf((st.v[m].x - prev.x) * kInvTwoPiF);
-                        j.b = (int)rintf((st.v[m].y - prev.y) * kInvTwoPiF);
-                    }
-                    any = any || (j.a != 0) || (j.b != 0);
-                    sj[fft_pos(x)] = j;
+            FCD_UNROLL
+            for (int m = 0; m < 16; ++m) {
+                const int x = t + TPF * m;
+                int2s j; j.a = 0; j.b = 0;
+                if (x > 0) {
+                    const cf prev = s0[fft_pos(x - 1)];
+                    j.a = (int)rintf((st.v[m].x - prev.x) * kInvTwoPiF);
+                    j.b = (int)rintf((st.v[m].y - prev.y) * kInvTwoPiF);
                 }
-                if (any) *flag = 1;
+                sj[fft_nat<TPF>(t, m)] = j;
             }
         } else if constexpr (PH == 6) {
-            if (p.unwrap && *flag) {   // inclusive scan of this thread's contiguous chunk
-                int a = 0, b = 0;
-                FCD_UNROLL
-                for (int q = 0; q < 16; ++q) {
-                    int2s j = sj[fft_pos(16 * t + q)];
-                    a += j.a; b += j.b;
-                    j.a = a; j.b = b;
-                    sj[fft_pos(16 * t + q)] = j;
-                }
-                int2s tot; tot.a = a; tot.b = b;
-                part[t] = tot;
+            int a = 0, b = 0;              // inclusive scan of this thread's contiguous chunk
+            FCD_UNROLL
+            for (int q = 0; q < 16; ++q) {
+                int2s j = sj[fft_pos(16 * t + q)];
+                a += j.a; b += j.b;
+                j.a = a; j.b = b;
+                sj[fft_pos(16 * t + q)] = j;
             }
+            int2s tot; tot.a = a; tot.b = b;
+            part[t] = tot;
         } else if constexpr (PH == 7) {
-            if (p.unwrap && *flag) {
-                int a = 0, b = 0;
-                for (int q = 0; q < t; ++q) { a += part[q].a; b += part[q].b; }
-                int2s o; o.a = a; o.b = b;
-                off[t] = o;
-            }
+            int a = 0, b = 0;
+            for (int q = 0; q < t; ++q) { a += part[q].a; b += part[q].b; }
+            int2s o; o.a = a; o.b = b;
+            off[t] = o;
         } else if constexpr (PH == 8) {
-            if (p.unwrap && *flag) {
-                const int2s cr = sj[fft_pos(p.x_ref)];
-                const int2s orf = off[p.x_ref >> 4];
-                const int ra = cr.a + orf.a, rb = cr.b + orf.b;
-                FCD_UNROLL
-                for (int m = 0; m < 16; ++m) {
-                    const int x = t + TPF * m;
-                    const int2s c = sj[fft_pos(x)];
-                    const int2s o = off[x >> 4];
-                    st.v[m].x -= kTwoPiF * (float)(c.a + o.a - ra);
-                    st.v[m].y -= kTwoPiF * (float)(c.b + o.b - rb);
-                }
+            const int2s cr = sj[fft_pos(p.x_ref)];
+            const int2s orf = off[p.x_ref >> 4];
+            const int ra = cr.a + orf.a, rb = cr.b + orf.b;
+            FCD_UNROLL
+            for (int m = 0; m < 16; ++m) {
+                const int x = t + TPF * m;
+                const int2s c = sj[fft_nat<TPF>(t, m)];
+                const int2s o = off[x >> 4];
+                st.v[m].x -= kTwoPiF * (float)(c.a + o.a - ra);
+                st.v[m].y -= kTwoPiF * (float)(c.b + o.b - rb);
             }
+        } else if constexpr (PH == 9) {
             if (p.phases) {
                 float* o0 = p.phases + (((long long)f * 2 + 0) * p.H + y) * W;
                 float* o1 = p.phases + (((long long)f * 2 + 1) * p.H + y) * W;
@@ -477,17 +488,30 @@ struct RowDemod {
                 }
             }
             FF::stepA(st.v, t, s0);
-        } else if constexpr (PH == 9) {
-            FF::stepB(st.v, t, s0, tw);
         } else if constexpr (PH == 10) {
+            FF::stepB(st.v, t, s0, tw);
+        } else if constexpr (PH == 11) {
             FF::stepC(st.v, t, s0);
         } else {
             FF::stepD(st.v, t, s0, tw);
+            // column-blocked store (see w3_index): two bases, constant strides
+            const int H = p.H;
+            cf* base = p.w3 + ((long long)f * w3_blocks(W) * H + y) * 4;
+            const long long step = (long long)TPF * H;                     // TPF/4 blocks of H*4 elements
+            const long long lo = (long long)(t >> 2) * H * 4 + (t & 3);     // slot = t + TPF*m, m < 8
+            const int s8 = W / 2 + t + (t > 0 ? 3 : 0);                     // kc = W/2 + t (m = 8)
+            const int sh = W / 2 + t + 3;                                   // kc = W/2 + t + TPF*(m-8), m > 8
+            const long long o8 = (long long)(s8 >> 2) * H * 4 + (s8 & 3);
+            const long long hi = (long long)(sh >> 2) * H * 4 + (sh & 3);
             FCD_UNROLL
-            for (int m = 0; m < 16; ++m) p.w3[w3_index(f, t + TPF * m, y, p.H, W)] = st.v[m];
+            for (int m = 0; m < 8; ++m) base[lo + m * step] = st.v[m];
+            base[o8] = st.v[8];
+            FCD_UNROLL
+            for (int m = 9; m < 16; ++m) base[hi + (m - 8) * step] = st.v[m];
         }
     }
 };
+
 
 
 // =========================================================================================
@@ -594,7 +618,7 @@ struct ColIntegrateParams {
 };
 
 template <int L, int G>
-struct ColIntegrate {
+struct ColIntegrate : AllPhases {
     using FF = Fft<L, -1, float>;
     using FI = Fft<L, +1, float>;
     using GL = GroupLayout<L, G, 2>;
@@ -745,7 +769,7 @@ struct RowInvParams {
 };
 
 template <int L, int G>
-struct RowInv {
+struct RowInv : AllPhases {
     using FI = Fft<L, +1, float>;
     using GL = GroupLayout<L, G>;
     using Params = RowInvParams;

@@ -39,7 +39,10 @@ inline void sync(stream_t) {}
 
 template <class K, int PH>
 inline void emu_phases(const typename K::Params& p, int bx, int by, unsigned char* smem, typename K::State* st) {
-    for (int tid = 0; tid < K::THREADS; ++tid) K::template phase<PH>(p, bx, by, tid, smem, st[tid]);
+    std::vector<char> on(K::THREADS);     // evaluated before the phase runs, like the device does
+    for (int tid = 0; tid < K::THREADS; ++tid) on[tid] = K::template enabled<PH>(p, smem, tid) ? 1 : 0;
+    for (int tid = 0; tid < K::THREADS; ++tid)
+        if (on[tid]) K::template phase<PH>(p, bx, by, tid, smem, st[tid]);
     if constexpr (PH + 1 < K::PHASES) emu_phases<K, PH + 1>(p, bx, by, smem, st);
 }
 
@@ -111,11 +114,12 @@ __device__ __forceinline__ void phase_barrier() {
 template <class K, int PH>
 __device__ __forceinline__ void run_phases(const typename K::Params& p, int bx, int by, unsigned char* smem,
                                            typename K::State& st) {
-    K::template phase<PH>(p, bx, by, (int)threadIdx.x, smem, st);
-    if constexpr (PH + 1 < K::PHASES) {
-        phase_barrier<K>();
-        run_phases<K, PH + 1>(p, bx, by, smem, st);
+    // a disabled phase is skipped together with its trailing barrier (uniform per barrier domain)
+    if (K::template enabled<PH>(p, smem, (int)threadIdx.x)) {
+        K::template phase<PH>(p, bx, by, (int)threadIdx.x, smem, st);
+        if constexpr (PH + 1 < K::PHASES) phase_barrier<K>();
     }
+    if constexpr (PH + 1 < K::PHASES) run_phases<K, PH + 1>(p, bx, by, smem, st);
 }
 
 // Persistent blocks: grid = min(tiles, SMs * resident blocks per SM); each block runs the
