@@ -344,8 +344,11 @@ struct RowDemod {
         cf w[16];   // carrier 1
     };
 
+    // the skip decision must be uniform over the barrier domain: one flag per group with
+    // per-group named barriers, one flag per block with block-wide barriers
     FCD_HD static int* group_flag(unsigned char* smem_all, int tid) {
-        unsigned char* gbase = smem_all + TW::TW_BYTES + (size_t)(tid / TPF) * GROUP_BYTES;
+        const int fg = (SYNC_THREADS != 0) ? tid / TPF : 0;
+        unsigned char* gbase = smem_all + TW::TW_BYTES + (size_t)fg * GROUP_BYTES;
         return reinterpret_cast<int*>(gbase + GL::GROUP_STRIDE * sizeof(cf)) + 4 * TPF;
     }
     // Phases 4..8 are the row unwrap.  A 2*pi jump between neighbours needs |phi| > pi/2
@@ -400,7 +403,7 @@ struct RowDemod {
         int* aux = reinterpret_cast<int*>(gbase + GL::GROUP_STRIDE * sizeof(cf));
         int2s* part = reinterpret_cast<int2s*>(aux);            // [TPF]
         int2s* off = reinterpret_cast<int2s*>(aux + 2 * TPF);   // [TPF]
-        int* flag = aux + 4 * TPF;
+        int* flag = group_flag(smem_all, tid);
         const int W = L;
         const int y = by * G + g;   // tiles are ordered frame-fastest so that consecutive tiles of
         const int f = bx;           // a block reuse the same theta rows out of L2
