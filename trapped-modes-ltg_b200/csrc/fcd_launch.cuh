@@ -41,6 +41,11 @@ template <class K, int PH>
 inline void emu_phases(const typename K::Params& p, int bx, int by, unsigned char* smem, typename K::State* st) {
     std::vector<char> on(K::THREADS);     // evaluated before the phase runs, like the device does
     for (int tid = 0; tid < K::THREADS; ++tid) on[tid] = K::template enabled<PH>(p, smem, tid) ? 1 : 0;
+    // a skipped phase also skips its barrier: the decision must be uniform over the barrier
+    // domain (whole block, or one group with named barriers) or the GPU deadlocks
+    const int dom = K::SYNC_THREADS == 0 ? K::THREADS : K::SYNC_THREADS;
+    for (int tid = 0; tid < K::THREADS; ++tid)
+        if (on[tid] != on[(tid / dom) * dom]) fail("emul: phase enable flag is not uniform over its barrier domain");
     for (int tid = 0; tid < K::THREADS; ++tid)
         if (on[tid]) K::template phase<PH>(p, bx, by, tid, smem, st[tid]);
     if constexpr (PH + 1 < K::PHASES) emu_phases<K, PH + 1>(p, bx, by, smem, st);
