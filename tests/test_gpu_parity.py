@@ -218,3 +218,23 @@ def test_errors_like_the_reference(api):
     assert fcd.height_from_layers(layers) == o.height_from_layers(layers)
     h1, _, _ = fcd.compute_height_map(ref, ref * 0.9 + 0.01, 1.0, layers)
     assert h1.shape == (256, 256)
+
+
+def test_cufft_pipeline_agrees(api):
+    """The cuFFT (torch.fft) version of the pipeline used as the benchmark comparator."""
+    torch = api["torch"]
+    from fcd_b200.cufft_pipeline import CufftPipeline
+    n = 512
+    ref = o.rotated_board(n, a=30.0, b=2.0)
+    frames = []
+    for peak in (0.5, 9.0):
+        _, uy, ux = o.gaussian_bump_displacement(n, (250.0, 270.0), 60.0, peak)
+        frames.append(o.rotated_board(n, a=30.0, b=2.0, uy=uy, ux=ux))
+    frames = torch.from_numpy(np.stack(frames)).cuda()
+    plan = api["eng"].HeightMapPlan((n, n), 2)
+    plan.bind(ref, square_size=o.board_square_size(n, 30.0), height=1.0)
+    ours = plan.execute(frames)
+    theirs = CufftPipeline(plan).execute(frames)
+    for i in range(2):
+        assert float(torch.linalg.vector_norm(ours[i] - theirs[i]) / torch.linalg.vector_norm(theirs[i])) < 2e-5
+    plan.close()
