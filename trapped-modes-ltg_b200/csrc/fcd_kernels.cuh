@@ -321,7 +321,7 @@ struct RowDemodParams {
 
 struct int2s { int a, b; };
 
-template <int L, int G>
+template <int L, int G, bool PRUNED = false>
 struct RowDemod {
     using FF = Fft<L, -1, float>;
     using FI = Fft<L, +1, float>;
@@ -409,10 +409,29 @@ struct RowDemod {
         const int f = bx;           // a block reuse the same theta rows out of L2
         if constexpr (PH == 0) {
             if (t == 0) *flag = 0;
-            load_band(p, f, 0, y, t, st.v);
-            load_band(p, f, 1, y, t, st.w);
-            FI::stepA(st.v, t, s0);
-            FI::stepA(st.w, t, s1);
+            if constexpr (PRUNED) {
+                // band no wider than W/8: every radix-8 butterfly of the first pass has at most
+                // one non-zero input -> one load and a few rotations per butterfly
+                constexpr int M1 = L / 8;
+                FCD_UNROLL
+                for (int i = 0; i < 2; ++i) {
+                    const cf* __restrict__ row = p.w2 + (((long long)f * 2 + i) * p.H + y) * p.ncp;
+                    const int p0 = p.kc0[i] & (W - 1);
+                    cf* sb = i == 0 ? s0 : s1;
+                    FCD_UNROLL
+                    for (int ii = 0; ii < 2; ++ii) {
+                        const int c = (t + TPF * ii - p0) & (M1 - 1);
+                        const int pp = (p0 + c) & (W - 1);
+                        const cf x = (c < p.nc[i]) ? row[c] : mk<float>(0.f, 0.f);
+                        FI::stepA_single(x, pp / M1, ii, t, sb);
+                    }
+                }
+            } else {
+                load_band(p, f, 0, y, t, st.v);
+                load_band(p, f, 1, y, t, st.w);
+                FI::stepA(st.v, t, s0);
+                FI::stepA(st.w, t, s1);
+            }
         } else if constexpr (PH == 1) {
             FI::stepB2(st.v, st.w, t, s0, s1, tw);
         } else if constexpr (PH == 2) {

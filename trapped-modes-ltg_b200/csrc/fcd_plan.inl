@@ -403,7 +403,14 @@ struct PlanImpl {
                 constexpr int G = Tune<L>::GDEM;
                 RowDemodParams p{w2.ptr, theta.ptr, w3.ptr, colphase.ptr, po, tw_w_f.ptr, H, ncp,
                                  {nc[0], nc[1]}, {c_lo[0] - W / 2, c_lo[1] - W / 2}, W / 2, unwrap ? 1 : 0};
-                launch<RowDemod<L, G>>(nf, H / G, s, p);
+                bool pruned = false;
+                if constexpr (Plan<L>::R1 == 8) {
+                    if (nc[0] <= L / 8 && nc[1] <= L / 8) {
+                        pruned = true;
+                        launch<RowDemod<L, G, true>>(nf, H / G, s, p);
+                    }
+                }
+                if (!pruned) launch<RowDemod<L, G, false>>(nf, H / G, s, p);
             })
             if (profiling) timer.mark(s, 2);
             launch<RowLink>(2, nf, s, RowLinkParams{colphase.ptr, rowoff.ptr, H, H / 2, unwrap ? 1 : 0});

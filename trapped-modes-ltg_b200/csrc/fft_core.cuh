@@ -267,6 +267,34 @@ struct Fft {
         }
     }
 
+    // ---- pruned first pass (radix 8): the butterfly `i` (= t + TPF*ii) has a single non-zero
+    // input x, sitting at input index r of the butterfly.  Its outputs are x * W_8^(DIR*r*k),
+    // k = 0..7: one inexact multiply (by W_8^r), the rest are exact quarter-turn rotations and
+    // sign flips.  Writes the same slots as stepA would.
+    FCD_HD static cx<T> quarter_turns(cx<T> v, int q) {   // v * i^q
+        const cx<T> a = (q & 1) ? mk<T>(-v.y, v.x) : v;
+        return (q & 2) ? mk<T>(-a.x, -a.y) : a;
+    }
+    FCD_HD static void stepA_single(cx<T> x, int r, int ii, int t, cx<T>* s) {
+        static_assert(R1 == 8, "pruned first pass is written for radix 8");
+        const T h = T(0.70710678118654752440);
+        // W_8^r = exp(DIR * i * pi * r / 4)
+        const int rr = r & 7;
+        const T c = (rr == 0) ? T(1) : (rr == 4) ? T(-1) : (rr == 2 || rr == 6) ? T(0) : ((rr == 1 || rr == 7) ? h : -h);
+        const T sn = (rr == 0 || rr == 4) ? T(0) : (rr == 2) ? T(1) : (rr == 6) ? T(-1) : ((rr < 4) ? h : -h);
+        const cx<T> u = mk<T>(c, DIR < 0 ? -sn : sn);
+        const int q = DIR < 0 ? ((4 - (rr & 3)) & 3) : (rr & 3);   // W_8^(2r) = (DIR*i)^r
+        const cx<T> x0 = x;
+        const cx<T> x1 = x * u;
+        const cx<T> x2 = quarter_turns(x0, q);
+        const cx<T> x3 = quarter_turns(x1, q);
+        const T sg = (rr & 1) ? T(-1) : T(1);                      // W_8^(4r) = (-1)^r
+        const int i = t + TPF * ii;
+        cx<T>* sb = s + fft_pos(i * R1);
+        sb[0] = x0; sb[1] = x1; sb[2] = x2; sb[3] = x3;
+        sb[4] = scale(x0, sg); sb[5] = scale(x1, sg); sb[6] = scale(x2, sg); sb[7] = scale(x3, sg);
+    }
+
     // ---- the four steps; a block-wide barrier is required between consecutive steps ----
     // A: v (natural ownership)  -> pass-1 butterflies -> smem
     FCD_HD static void stepA(cx<T>* v, int t, cx<T>* s) {
