@@ -147,14 +147,40 @@ struct RowFwd : AllPhases {
     using GL = GroupLayout<L, G>;
     using Params = RowFwdParams;
     static constexpr bool BLOCKED_TILES = false;
-    static constexpr bool PIPELINED = false;
+    static constexpr bool PIPELINED = true;
     static constexpr int SYNC_THREADS = 0;   // 0: block-wide barrier
     static constexpr int MIN_BLOCKS = ((G * L / 16) <= 128 ? 6 : ((G * L / 16) <= 256 ? 3 : 1));
     static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 6;
     using TW = SmemTwiddles<F, THREADS>;
     static constexpr int SMEM_BYTES = TW::TW_BYTES + G * GL::STRIDE * (int)sizeof(cf);
     FCD_HD static void prologue(const Params& p, int tid, unsigned char* smem) { TW::load(p.tw, tid, smem); }
-    struct State { cf v[16]; };
+    struct State { cf v[16]; TileLink link; };
+
+    // two image rows -> one complex sequence (mask substitution analyze.py:231 fused)
+    FCD_HD static void load_rows(const Params& p, int bx, int by, int g, int t, cf* v) {
+        const int W = L;
+        const int ya = (bx * G + g) * 2;
+        const long long base = ((long long)by * p.H + ya) * W;
+        const float* __restrict__ fa = p.frames + base;
+        const float* __restrict__ fb = fa + W;
+        if (p.mask) {
+            const uint8_t* ma = p.mask + (long long)by * p.mask_stride + (long long)ya * W;
+            const uint8_t* mb = ma + W;
+            const float* ra = p.reference + (long long)ya * W;
+            const float* rb = ra + W;
+            FCD_UNROLL
+            for (int m = 0; m < 16; ++m) {
+                const int x = t + TPF * m;
+                v[m] = mk<float>(ma[x] ? ra[x] : fa[x], mb[x] ? rb[x] : fb[x]);
+            }
+        } else {
+            FCD_UNROLL
+            for (int m = 0; m < 16; ++m) {
+                const int x = t + TPF * m;
+                v[m] = mk<float>(fa[x], fb[x]);
+            }
+        }
+    }
 
     template <int PH>
     FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem_all, State& st) {
@@ -164,27 +190,7 @@ struct RowFwd : AllPhases {
         cf* s = reinterpret_cast<cf*>(smem) + g * GL::STRIDE;
         const int W = L;
         if constexpr (PH == 0) {
-            const int ya = (bx * G + g) * 2;
-            const long long base = ((long long)by * p.H + ya) * W;
-            const float* fa = p.frames + base;
-            const float* fb = fa + W;
-            if (p.mask) {
-                const uint8_t* ma = p.mask + (long long)by * p.mask_stride + (long long)ya * W;
-                const uint8_t* mb = ma + W;
-                const float* ra = p.reference + (long long)ya * W;
-                const float* rb = ra + W;
-                FCD_UNROLL
-                for (int m = 0; m < 16; ++m) {
-                    const int x = t + TPF * m;
-                    st.v[m] = mk<float>(ma[x] ? ra[x] : fa[x], mb[x] ? rb[x] : fb[x]);
-                }
-            } else {
-                FCD_UNROLL
-                for (int m = 0; m < 16; ++m) {
-                    const int x = t + TPF * m;
-                    st.v[m] = mk<float>(fa[x], fb[x]);
-                }
-            }
+            if (st.link.first) load_rows(p, bx, by, g, t, st.v);   // later tiles were prefetched in phase 5
             F::stepA(st.v, t, s);
         } else if constexpr (PH == 1) {
             F::stepB(st.v, t, s, tw);
@@ -196,6 +202,9 @@ struct RowFwd : AllPhases {
             FCD_UNROLL
             for (int m = 0; m < 16; ++m) s[fft_nat<TPF>(t, m)] = st.v[m];
         } else {
+            // the data registers are dead from here on: fetch the next tile's rows into them
+            // while this phase and the loop barrier run
+            if (st.link.has_next) load_rows(p, st.link.next_bx, st.link.next_by, g, t, st.v);
             const cf* sb = reinterpret_cast<const cf*>(smem);
             const int total = 2 * p.ncp * G;
             for (int item = tid; item < total; item += THREADS) {
@@ -328,7 +337,7 @@ struct RowDemod {
     using GL = GroupLayout<L, G, 2>;
     using Params = RowDemodParams;
     static constexpr bool BLOCKED_TILES = true;
-    static constexpr bool PIPELINED = false;
+    static constexpr bool PIPELINED = true;
     static constexpr int SYNC_THREADS = (L / 16 >= 32 && G > 1 && G <= 15) ? L / 16 : 0;   // per-group named barriers
     static constexpr int MIN_BLOCKS = ((G * L / 16) <= 128 ? 4 : ((G * L / 16) <= 256 ? 2 : 1));
     static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 13;
@@ -342,7 +351,17 @@ struct RowDemod {
     struct State {
         cf v[16];   // carrier 0, later (phi0, phi1)
         cf w[16];   // carrier 1
+        cf nx[4];   // pruned path: the four band values of the next tile (prefetched)
+        TileLink link;
     };
+
+    // the single non-zero input of first-pass butterfly ii of carrier i (pruned path)
+    FCD_HD static cf band_value(const Params& p, int f, int i, int y, int t, int ii) {
+        constexpr int M1 = L / 8;
+        const cf* __restrict__ row = p.w2 + (((long long)f * 2 + i) * p.H + y) * p.ncp;
+        const int c = (t + TPF * ii - (p.kc0[i] & (L - 1))) & (M1 - 1);
+        return (c < p.nc[i]) ? row[c] : mk<float>(0.f, 0.f);
+    }
 
     // the skip decision must be uniform over the barrier domain: one flag per group with
     // per-group named barriers, one flag per block with block-wide barriers
@@ -413,17 +432,19 @@ struct RowDemod {
                 // band no wider than W/8: every radix-8 butterfly of the first pass has at most
                 // one non-zero input -> one load and a few rotations per butterfly
                 constexpr int M1 = L / 8;
+                if (st.link.first) {      // later tiles were prefetched in phase 9
+                    FCD_UNROLL
+                    for (int q = 0; q < 4; ++q) st.nx[q] = band_value(p, f, q >> 1, y, t, q & 1);
+                }
                 FCD_UNROLL
                 for (int i = 0; i < 2; ++i) {
-                    const cf* __restrict__ row = p.w2 + (((long long)f * 2 + i) * p.H + y) * p.ncp;
                     const int p0 = p.kc0[i] & (W - 1);
                     cf* sb = i == 0 ? s0 : s1;
                     FCD_UNROLL
                     for (int ii = 0; ii < 2; ++ii) {
                         const int c = (t + TPF * ii - p0) & (M1 - 1);
                         const int pp = (p0 + c) & (W - 1);
-                        const cf x = (c < p.nc[i]) ? row[c] : mk<float>(0.f, 0.f);
-                        FI::stepA_single(x, pp / M1, ii, t, sb);
+                        FI::stepA_single(st.nx[i * 2 + ii], pp / M1, ii, t, sb);
                     }
                 }
             } else {
@@ -510,6 +531,13 @@ struct RowDemod {
                 }
             }
             FF::stepA(st.v, t, s0);
+            if constexpr (PRUNED) {
+                if (st.link.has_next) {   // next tile: frame-fastest order, same group -> same row offset g
+                    const int nf = st.link.next_bx, ny = st.link.next_by * G + g;
+                    FCD_UNROLL
+                    for (int q = 0; q < 4; ++q) st.nx[q] = band_value(p, nf, q >> 1, ny, t, q & 1);
+                }
+            }
         } else if constexpr (PH == 10) {
             FF::stepB(st.v, t, s0, tw);
         } else if constexpr (PH == 11) {
