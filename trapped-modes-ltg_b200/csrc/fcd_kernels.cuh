@@ -337,7 +337,7 @@ struct RowDemod {
     using GL = GroupLayout<L, G, 2>;
     using Params = RowDemodParams;
     static constexpr bool BLOCKED_TILES = true;
-    static constexpr bool PIPELINED = true;
+    static constexpr bool PIPELINED = false;
     static constexpr int SYNC_THREADS = (L / 16 >= 32 && G > 1 && G <= 15) ? L / 16 : 0;   // per-group named barriers
     static constexpr int MIN_BLOCKS = ((G * L / 16) <= 128 ? 4 : ((G * L / 16) <= 256 ? 2 : 1));
     static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 13;
@@ -351,8 +351,6 @@ struct RowDemod {
     struct State {
         cf v[16];   // carrier 0, later (phi0, phi1)
         cf w[16];   // carrier 1
-        cf nx[4];   // pruned path: the four band values of the next tile (prefetched)
-        TileLink link;
     };
 
     // the single non-zero input of first-pass butterfly ii of carrier i (pruned path)
@@ -432,10 +430,9 @@ struct RowDemod {
                 // band no wider than W/8: every radix-8 butterfly of the first pass has at most
                 // one non-zero input -> one load and a few rotations per butterfly
                 constexpr int M1 = L / 8;
-                if (st.link.first) {      // later tiles were prefetched in phase 9
-                    FCD_UNROLL
-                    for (int q = 0; q < 4; ++q) st.nx[q] = band_value(p, f, q >> 1, y, t, q & 1);
-                }
+                cf nx[4];
+                FCD_UNROLL
+                for (int q = 0; q < 4; ++q) nx[q] = band_value(p, f, q >> 1, y, t, q & 1);   // loads first
                 FCD_UNROLL
                 for (int i = 0; i < 2; ++i) {
                     const int p0 = p.kc0[i] & (W - 1);
@@ -444,7 +441,7 @@ struct RowDemod {
                     for (int ii = 0; ii < 2; ++ii) {
                         const int c = (t + TPF * ii - p0) & (M1 - 1);
                         const int pp = (p0 + c) & (W - 1);
-                        FI::stepA_single(st.nx[i * 2 + ii], pp / M1, ii, t, sb);
+                        FI::stepA_single(nx[i * 2 + ii], pp / M1, ii, t, sb);
                     }
                 }
             } else {
@@ -531,13 +528,6 @@ struct RowDemod {
                 }
             }
             FF::stepA(st.v, t, s0);
-            if constexpr (PRUNED) {
-                if (st.link.has_next) {   // next tile: frame-fastest order, same group -> same row offset g
-                    const int nf = st.link.next_bx, ny = st.link.next_by * G + g;
-                    FCD_UNROLL
-                    for (int q = 0; q < 4; ++q) st.nx[q] = band_value(p, nf, q >> 1, ny, t, q & 1);
-                }
-            }
         } else if constexpr (PH == 10) {
             FF::stepB(st.v, t, s0, tw);
         } else if constexpr (PH == 11) {
