@@ -73,6 +73,23 @@ int fcd_execute(fcd_plan* plan, const float* frames_dev, int n_frames, float* he
                 float* phases_dev, const uint8_t* mask_dev, long long mask_stride, int unwrap,
                 void* stream);
 
+/* Same as fcd_execute for camera frames that are still integers: frame_dtype 0 = float32,
+ * 1 = uint8, 2 = uint16.  Replaces the `.astype(np.float32)` of analyze.load_image
+ * (pydata/analyze.py:40) in front of the path: the widening happens in the first kernel's loads. */
+int fcd_execute_typed(fcd_plan* plan, const void* frames_dev, int frame_dtype, int n_frames, float* height_dev,
+                      float* phases_dev, const uint8_t* mask_dev, long long mask_stride, int unwrap,
+                      void* stream);
+
+/* Change the effective height (pyfcd/fcd.py:16-25, :32) of a bound plan without redoing the
+ * per-reference work. */
+int fcd_set_height(fcd_plan* plan, double height);
+
+/* Residue guard: for each of n_maps phase maps (rows*cols float32 each, e.g. the phases output
+ * of fcd_execute with unwrap = 0) the number of 2x2 loops whose wrapped differences do not sum
+ * to zero.  The unwrapped phases equal scikit-image's unwrap_phase (pyfcd/fcd.py:119) up to a
+ * global 2*pi*k only where this is zero.  counts_out: n_maps ints on the host. */
+int fcd_count_residues(fcd_plan* plan, const float* phases_dev, int n_maps, int* counts_out, void* stream);
+
 /* Carrier attributes (pyfcd/carriers.py:14-15): boolean mask in unshifted layout and ccsgn
  * as complex128 (as_c128 != 0) or complex64. */
 int fcd_get_carrier_mask(fcd_plan* plan, int carrier, uint8_t* mask_dev, void* stream);

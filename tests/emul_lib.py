@@ -89,18 +89,31 @@ class EmulPlan:
                                                             float(radius), float(cal), float(height), None))
 
     def execute(self, frames, phases=False, mask=None, unwrap=True):
-        fr = np.ascontiguousarray(frames, dtype=np.float32)
+        fr = np.ascontiguousarray(frames)
+        if fr.dtype not in (np.uint8, np.uint16):
+            fr = np.ascontiguousarray(fr, dtype=np.float32)
+        kind = {np.dtype(np.float32): 0, np.dtype(np.uint8): 1, np.dtype(np.uint16): 2}[fr.dtype]
         if fr.ndim == 2:
             fr = fr[None]
-        out = np.zeros_like(fr)
+        out = np.zeros(fr.shape, np.float32)
         ph = np.zeros((fr.shape[0], 2) + self.shape, np.float32) if phases else None
         mk, stride = None, 0
         if mask is not None:
             mk = np.ascontiguousarray(mask, dtype=np.uint8)
             stride = self.shape[0] * self.shape[1] if mk.ndim == 3 else 0
-        _native.check(self.lib, self.lib.fcd_execute(self.h, _p(fr), fr.shape[0], _p(out), _p(ph), _p(mk), stride,
-                                                     int(unwrap), None))
+        _native.check(self.lib, self.lib.fcd_execute_typed(self.h, _p(fr), kind, fr.shape[0], _p(out), _p(ph), _p(mk),
+                                                           stride, int(unwrap), None))
         return (out, ph) if phases else out
+
+    def set_height(self, height):
+        _native.check(self.lib, self.lib.fcd_set_height(self.h, float(height)))
+
+    def count_residues(self, phases):
+        ph = np.ascontiguousarray(phases, dtype=np.float32)
+        n = ph.size // (self.shape[0] * self.shape[1])
+        out = (ctypes.c_int * max(n, 1))()
+        _native.check(self.lib, self.lib.fcd_count_residues(self.h, _p(ph), n, out, None))
+        return [out[i] for i in range(n)]
 
     def mask(self, i):
         m = np.zeros(self.shape, np.uint8)

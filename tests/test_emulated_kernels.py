@@ -172,3 +172,35 @@ def test_error_behaviour():
     rc = l.fcd_execute(plan.h, f.ctypes.data, 1, f.ctypes.data, None, None, 0, 1, None)
     assert rc == _native.FCD_ERR_STATE                                                       # execute before bind
     plan.close()
+
+
+def test_integer_camera_frames_and_set_height(golden):
+    """uint8 / uint16 frames are widened in the first kernel (analyze.load_image's astype)."""
+    g = lambda k: golden[f"synth256_small.{k}"]
+    ref8 = np.round(g("ref") * 200).astype(np.uint8)
+    frm8 = np.round(g("frame") * 200).astype(np.uint8)
+    sq = float(g("square_size"))
+    plan = EmulPlan((256, 256))
+    bind_like_reference(plan, ref8.astype(np.float32), sq)
+    h_f32 = plan.execute(frm8.astype(np.float32))
+    h_u8 = plan.execute(frm8)
+    h_u16 = plan.execute(frm8.astype(np.uint16) * 1)
+    assert np.array_equal(h_u8, h_f32) and np.array_equal(h_u16, h_f32)
+    hmo, _, _ = o.compute_height_map(ref8.astype(np.float32), frm8.astype(np.float32), sq, height=1.0)
+    assert rel_l2(h_u8[0], hmo) < 1e-5
+    plan.set_height(0.25)
+    assert rel_l2(plan.execute(frm8)[0], hmo / 0.25) < 1e-5
+    plan.close()
+
+
+def test_residue_guard(golden):
+    g = lambda k: golden[f"synth256_wrap.{k}"]
+    plan = EmulPlan((256, 256))
+    bind_like_reference(plan, g("ref").astype(np.float64), float(g("square_size")))
+    _, ph = plan.execute(g("frame"), phases=True, unwrap=False)
+    assert plan.count_residues(ph[0]) == [0, 0] == list(g("residues"))
+    rng = np.random.default_rng(3)
+    noisy = rng.uniform(-np.pi, np.pi, (2, 256, 256)).astype(np.float32)
+    got = plan.count_residues(noisy)
+    assert got == [o.count_residues(noisy[0]), o.count_residues(noisy[1])] and got[0] > 1000
+    plan.close()

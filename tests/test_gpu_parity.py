@@ -238,3 +238,35 @@ def test_cufft_pipeline_agrees(api):
     for i in range(2):
         assert float(torch.linalg.vector_norm(ours[i] - theirs[i]) / torch.linalg.vector_norm(theirs[i])) < 2e-5
     plan.close()
+
+
+def test_integer_frames_residues_and_reference_cache(api, golden):
+    torch = api["torch"]
+    g = lambda k: golden[f"synth256_small.{k}"]
+    ref8 = np.round(g("ref") * 200).astype(np.uint8)
+    frm8 = np.round(g("frame") * 200).astype(np.uint8)
+    sq = float(g("square_size"))
+    hm8, _, cal = api["eng"].compute_height_maps(ref8.astype(np.float32), frm8[None], sq, height=1.0)
+    hmf, _, _ = api["eng"].compute_height_maps(ref8.astype(np.float32), frm8[None].astype(np.float32), sq, height=1.0)
+    assert torch.equal(hm8, hmf)
+    hmo, _, _ = o.compute_height_map(ref8.astype(np.float32), frm8.astype(np.float32), sq, height=1.0)
+    assert rel_l2(hm8[0].cpu().numpy(), hmo) < 1e-5
+    # residue guard on wrapped phases
+    plan = api["eng"].HeightMapPlan((256, 256), 1)
+    gw = lambda k: golden[f"synth256_wrap.{k}"]
+    plan.bind(gw("ref"), square_size=float(gw("square_size")), height=1.0)
+    _, ph = plan.execute(torch.from_numpy(gw("frame")).cuda(), phases=True, unwrap=False)
+    assert plan.count_residues(ph) == [0, 0]
+    noisy = torch.rand((256, 256), device="cuda") * 6.2 - 3.1
+    assert plan.count_residues(noisy) == [o.count_residues(noisy.cpu().numpy())]
+    plan.close()
+    # drop-in: second call with the same reference reuses the bound state, a new height is honoured
+    fcd = api["fcd"]
+    a, _, _ = fcd.compute_height_map(g("ref"), g("frame"), sq, height=1.0)
+    n0 = api["eng"].get_plan((256, 256), 1).launch_count
+    b, _, _ = fcd.compute_height_map(g("ref").copy(), g("frame"), sq, height=0.5)
+    n1 = api["eng"].get_plan((256, 256), 1).launch_count
+    assert n1 - n0 <= 7                      # only the per-frame kernels ran
+    assert np.allclose(b, a / 0.5, rtol=1e-6, atol=1e-9)
+    c, _, _ = fcd.compute_height_map(g("ref") * 0.5, g("frame") * 0.5, sq, height=1.0)   # different reference -> re-bind
+    assert rel_l2(c, a) < 1e-5

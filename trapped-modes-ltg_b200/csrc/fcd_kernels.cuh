@@ -130,7 +130,8 @@ struct NoPrologue : AllPhases {
 //     fall inside the two carrier disks, transposed:  w1[f][i][c'][y]  (y contiguous)
 // =========================================================================================
 struct RowFwdParams {
-    const float* frames;      // [F][H][W]
+    const void* frames;       // [F][H][W] float32 / uint8 / uint16 (frame_kind 0 / 1 / 2)
+    int frame_kind;
     const float* reference;   // [H][W]   (mask substitution, may be null)
     const uint8_t* mask;      // [F][H][W] or [H][W] (mask_stride = 0), may be null
     long long mask_stride;    // elements between consecutive frames' masks
@@ -156,13 +157,15 @@ struct RowFwd : AllPhases {
     FCD_HD static void prologue(const Params& p, int tid, unsigned char* smem) { TW::load(p.tw, tid, smem); }
     struct State { cf v[16]; TileLink link; };
 
-    // two image rows -> one complex sequence (mask substitution analyze.py:231 fused)
-    FCD_HD static void load_rows(const Params& p, int bx, int by, int g, int t, cf* v) {
+    // two image rows -> one complex sequence (mask substitution analyze.py:231 fused); camera
+    // frames may be passed as uint8 / uint16 and are widened on load (analyze.load_image's astype)
+    template <class PT>
+    FCD_HD static void load_rows_t(const Params& p, int bx, int by, int g, int t, cf* v) {
         const int W = L;
         const int ya = (bx * G + g) * 2;
         const long long base = ((long long)by * p.H + ya) * W;
-        const float* __restrict__ fa = p.frames + base;
-        const float* __restrict__ fb = fa + W;
+        const PT* __restrict__ fa = reinterpret_cast<const PT*>(p.frames) + base;
+        const PT* __restrict__ fb = fa + W;
         if (p.mask) {
             const uint8_t* ma = p.mask + (long long)by * p.mask_stride + (long long)ya * W;
             const uint8_t* mb = ma + W;
@@ -171,15 +174,20 @@ struct RowFwd : AllPhases {
             FCD_UNROLL
             for (int m = 0; m < 16; ++m) {
                 const int x = t + TPF * m;
-                v[m] = mk<float>(ma[x] ? ra[x] : fa[x], mb[x] ? rb[x] : fb[x]);
+                v[m] = mk<float>(ma[x] ? ra[x] : (float)fa[x], mb[x] ? rb[x] : (float)fb[x]);
             }
         } else {
             FCD_UNROLL
             for (int m = 0; m < 16; ++m) {
                 const int x = t + TPF * m;
-                v[m] = mk<float>(fa[x], fb[x]);
+                v[m] = mk<float>((float)fa[x], (float)fb[x]);
             }
         }
+    }
+    FCD_HD static void load_rows(const Params& p, int bx, int by, int g, int t, cf* v) {
+        if (p.frame_kind == 0) load_rows_t<float>(p, bx, by, g, t, v);
+        else if (p.frame_kind == 1) load_rows_t<uint8_t>(p, bx, by, g, t, v);
+        else load_rows_t<uint16_t>(p, bx, by, g, t, v);
     }
 
     template <int PH>
@@ -633,6 +641,44 @@ struct PhaseFix : NoPrologue {
         if (o != 0.f) {
             float* row = p.phases + ((long long)by * p.H + bx) * p.W;
             for (int x = tid; x < p.W; x += THREADS) row[x] += o;
+        }
+    }
+};
+
+// Residue guard: number of 2x2 loops of a phase map whose wrapped differences do
+// not sum to zero.  Parity of the unwrapped phases with the reference's unwrapper is defined
+// only when this is zero.
+struct ResidueParams {
+    const float* phases;   // [M][H][W]
+    int* counts;           // [M], zero-initialised
+    int H, W;
+};
+struct ResidueCount : NoPrologue {
+    using Params = ResidueParams;
+    static constexpr bool BLOCKED_TILES = false;
+    static constexpr bool PIPELINED = false;
+    static constexpr int SYNC_THREADS = 0;
+    static constexpr int MIN_BLOCKS = 1;
+    static constexpr int THREADS = 256, PHASES = 1, SMEM_BYTES = 16;
+    struct State { int dummy; };
+    FCD_HD static float wrapd(float d) { return d - kTwoPiF * rintf(d * kInvTwoPiF); }
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
+        // bx: row y (0..H-2), by: map
+        const float* r0 = p.phases + ((long long)by * p.H + bx) * p.W;
+        const float* r1 = r0 + p.W;
+        int n = 0;
+        for (int x = tid; x + 1 < p.W; x += THREADS) {
+            const float s = wrapd(r0[x + 1] - r0[x]) + wrapd(r1[x + 1] - r0[x + 1]) + wrapd(r1[x] - r1[x + 1]) +
+                            wrapd(r0[x] - r1[x]);
+            if (rintf(s * kInvTwoPiF) != 0.f) ++n;
+        }
+        if (n) {
+#if defined(__CUDA_ARCH__)
+            atomicAdd(p.counts + by, n);
+#else
+            p.counts[by] += n;
+#endif
         }
     }
 };

@@ -370,8 +370,10 @@ struct PlanImpl {
     }
 
     // ------------------------------------------------------------------ execute ----
-    void execute(const float* frames, int n_frames, float* height_out, float* phases, const uint8_t* mask,
-                 long long mask_stride, int unwrap, rt::stream_t s) {
+    void execute(const void* frames, int frame_kind, int n_frames, float* height_out, float* phases,
+                 const uint8_t* mask, long long mask_stride, int unwrap, rt::stream_t s) {
+        if (frame_kind < 0 || frame_kind > 2) rt::fail("frame dtype must be 0 (float32), 1 (uint8) or 2 (uint16)");
+        const size_t px = frame_kind == 0 ? 4 : (frame_kind == 1 ? 1 : 2);
         if (!bound) throw std::logic_error("fcd_execute called before fcd_bind_reference");
         if (n_frames < 0) rt::fail("negative frame count");
         if (det == 0.0) rt::fail("carriers are collinear (singular 2x2 system)");
@@ -380,14 +382,14 @@ struct PlanImpl {
         const float scale_int = (float)(1.0 / (2.0 * height * det * (double)H * (double)W));
         for (int f0 = 0; f0 < n_frames; f0 += chunk) {
             const int nf = std::min(chunk, n_frames - f0);
-            const float* fr = frames + (long long)f0 * n;
+            const void* fr = static_cast<const unsigned char*>(frames) + (size_t)f0 * n * px;
             float* ho = height_out + (long long)f0 * n;
             float* po = phases ? phases + (long long)f0 * 2 * n : nullptr;
             const uint8_t* mk_ = mask ? mask + (long long)f0 * mask_stride : nullptr;
             if (profiling) timer.begin_chunk(s, nf);
             FCD_DISPATCH_L(W, {
                 constexpr int G = Tune<L>::GROW;
-                RowFwdParams p{fr, nullptr, mk_, mask_stride, w1.ptr, tw_w_f.ptr, H, ncp,
+                RowFwdParams p{fr, frame_kind, nullptr, mk_, mask_stride, w1.ptr, tw_w_f.ptr, H, ncp,
                                {nc[0], nc[1]}, {c_lo[0] - W / 2, c_lo[1] - W / 2}};
                 p.reference = reference_f32();
                 launch<RowFwd<L, G>>(H / (2 * G), nf, s, p);
@@ -550,7 +552,34 @@ int fcd_execute(fcd_plan* plan, const float* frames_dev, int n_frames, float* he
                 const uint8_t* mask_dev, long long mask_stride, int unwrap, void* stream) {
     if (!plan || (n_frames > 0 && (!frames_dev || !height_dev))) { g_fcd_error = "null argument"; return FCD_ERR_INVALID; }
     return fcd_guard([&] {
-        plan->impl.execute(frames_dev, n_frames, height_dev, phases_dev, mask_dev, mask_stride, unwrap, stream);
+        plan->impl.execute(frames_dev, 0, n_frames, height_dev, phases_dev, mask_dev, mask_stride, unwrap, stream);
+    });
+}
+
+int fcd_execute_typed(fcd_plan* plan, const void* frames_dev, int frame_dtype, int n_frames, float* height_dev,
+                      float* phases_dev, const uint8_t* mask_dev, long long mask_stride, int unwrap, void* stream) {
+    if (!plan || (n_frames > 0 && (!frames_dev || !height_dev))) { g_fcd_error = "null argument"; return FCD_ERR_INVALID; }
+    return fcd_guard([&] {
+        plan->impl.execute(frames_dev, frame_dtype, n_frames, height_dev, phases_dev, mask_dev, mask_stride, unwrap, stream);
+    });
+}
+
+int fcd_set_height(fcd_plan* plan, double height) {
+    if (!plan) { g_fcd_error = "null plan"; return FCD_ERR_INVALID; }
+    return fcd_guard([&] { plan->impl.set_height(height); });
+}
+
+int fcd_count_residues(fcd_plan* plan, const float* phases_dev, int n_maps, int* counts_out, void* stream) {
+    if (!plan || !phases_dev || !counts_out || n_maps < 0) { g_fcd_error = "bad argument"; return FCD_ERR_INVALID; }
+    return fcd_guard([&] {
+        auto& im = plan->impl;
+        fcd::rt::DevBuf<int> counts;
+        counts.alloc((size_t)std::max(n_maps, 1));
+        fcd::rt::dmemset(counts.ptr, 0, sizeof(int) * (size_t)std::max(n_maps, 1), stream);
+        if (n_maps > 0) {
+            im.launch<fcd::ResidueCount>(im.H - 1, n_maps, stream, fcd::ResidueParams{phases_dev, counts.ptr, im.H, im.W});
+            fcd::rt::d2h(counts_out, counts.ptr, sizeof(int) * (size_t)n_maps, stream);
+        }
     });
 }
 

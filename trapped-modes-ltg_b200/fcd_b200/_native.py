@@ -30,6 +30,10 @@ PROTOTYPES = {
                                           ctypes.c_double, ctypes.c_double, ctypes.c_void_p]),
     "fcd_execute": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                    ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p]),
+    "fcd_execute_typed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p]),
+    "fcd_set_height": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double]),
+    "fcd_count_residues": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, c_int_p, ctypes.c_void_p]),
     "fcd_get_carrier_mask": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "fcd_get_carrier_ccsgn": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "fcd_fft2_c128": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),

@@ -224,15 +224,18 @@ class HeightMapPlan:
                 mask: Optional[torch.Tensor] = None, unwrap: bool = True):
         """frames: CUDA float32 [n, H, W] (or [H, W]).  Returns height maps float32 [n, H, W]
         and, when ``phases`` is True or a tensor, phases float32 [n, 2, H, W]."""
-        if not (isinstance(frames, torch.Tensor) and frames.is_cuda and frames.dtype == torch.float32):
-            raise TypeError("frames must be a CUDA float32 tensor (see compute_height_maps for numpy input)")
+        kinds = {torch.float32: 0, torch.uint8: 1, torch.uint16: 2}
+        if not (isinstance(frames, torch.Tensor) and frames.is_cuda and frames.dtype in kinds):
+            raise TypeError("frames must be a CUDA float32 / uint8 / uint16 tensor "
+                            "(see compute_height_maps for numpy input)")
+        kind = kinds[frames.dtype]
         squeeze = frames.dim() == 2
         fr = frames.unsqueeze(0) if squeeze else frames
         fr = fr.contiguous()
         self._check_image(fr)
         n = fr.shape[0]
         if out is None:
-            out = torch.empty_like(fr)
+            out = torch.empty(fr.shape, dtype=torch.float32, device=fr.device)
         elif not (out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.numel() == fr.numel()):
             raise ValueError("out must be a contiguous CUDA float32 tensor of the frames' size")
         ph = None
@@ -252,12 +255,29 @@ class HeightMapPlan:
                 mask_stride = self.shape[0] * self.shape[1]
             self._check_image(mk)
         with torch.cuda.device(self.device):
-            check(self.lib, self.lib.fcd_execute(self._h, _ptr(fr), int(n), _ptr(out), _ptr(ph), _ptr(mk),
-                                                 int(mask_stride), int(bool(unwrap)), _stream_ptr()))
+            check(self.lib, self.lib.fcd_execute_typed(self._h, _ptr(fr), kind, int(n), _ptr(out), _ptr(ph), _ptr(mk),
+                                                       int(mask_stride), int(bool(unwrap)), _stream_ptr()))
         if squeeze:
             out = out.view(self.shape) if out.dim() == 3 else out
             ph = ph[0] if ph is not None else None
         return (out, ph) if ph is not None else out
+
+    def set_height(self, layers=None, height=None) -> None:
+        """Change the effective height of the bound reference (fcd.py:16-25) without re-binding."""
+        h_eff = resolve_height(layers, height)
+        check(self.lib, self.lib.fcd_set_height(self._h, float(h_eff)))
+        self.height = h_eff
+
+    def count_residues(self, phases: torch.Tensor) -> list:
+        """Residues per phase map ([..., H, W] CUDA float32, e.g. wrapped phases from
+        execute(..., phases=True, unwrap=False)); unwrap parity with the reference holds where 0."""
+        ph = phases.to(self.device).to(torch.float32).contiguous()
+        self._check_image(ph)
+        n = ph.numel() // (self.shape[0] * self.shape[1])
+        out = (ctypes.c_int * max(n, 1))()
+        with torch.cuda.device(self.device):
+            check(self.lib, self.lib.fcd_count_residues(self._h, _ptr(ph), int(n), out, _stream_ptr()))
+        return [out[i] for i in range(n)]
 
     STAGES = ("row_fwd", "col_band", "row_demod", "row_link", "phase_fix", "col_integrate", "row_inv")
 
@@ -323,7 +343,9 @@ def compute_height_maps(reference, frames, square_size, layers=None, height=None
         plan = get_plan(shape, frames_per_launch)
     cal = plan.bind(reference, square_size=square_size, layers=layers, height=height)
     if isinstance(frames, torch.Tensor) and frames.is_cuda:
-        fr = frames.to(torch.float32)
+        fr = frames if frames.dtype in (torch.uint8, torch.uint16) else frames.to(torch.float32)
+    elif isinstance(frames, np.ndarray) and frames.dtype in (np.uint8, np.uint16):
+        fr = torch.from_numpy(np.ascontiguousarray(frames)).to(plan.device)    # widened on the GPU
     else:
         fr = to_device_image(frames, plan.device, allow_f64=False)
     res = plan.execute(fr, out=out, phases=return_phases, mask=mask, unwrap=unwrap)
