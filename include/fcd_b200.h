@@ -90,6 +90,19 @@ int fcd_set_height(fcd_plan* plan, double height);
  * global 2*pi*k only where this is zero.  counts_out: n_maps ints on the host. */
 int fcd_count_residues(fcd_plan* plan, const float* phases_dev, int n_maps, int* counts_out, void* stream);
 
+/* Floating-structure mask of each frame: box filter of width `smoothed`, threshold at the mean of
+ * the filtered image, largest 8-connected region below it.  Bit-exact replacement of
+ * analyze.mask (pydata/analyze.py:43-100).  frames_dev [n][rows][cols] float32 ->
+ * mask_dev [n][rows][cols] uint8 (1 inside the structure). */
+int fcd_structure_mask(fcd_plan* plan, const float* frames_dev, int n_frames, int smoothed, uint8_t* mask_dev,
+                       void* stream);
+
+/* Centre of the structure's cavity: int(centroid) of the largest 8-connected region of ~mask
+ * whose bounding box does not touch the border.  Replaces analyze.center
+ * (pydata/analyze.py:104-140).  centers_out: 2*n ints on the host, (cy, cx) per frame, or
+ * (-1, -1) where the reference would fail for lack of an enclosed region. */
+int fcd_mask_center(fcd_plan* plan, const uint8_t* mask_dev, int n_frames, int* centers_out, void* stream);
+
 /* Carrier attributes (pyfcd/carriers.py:14-15): boolean mask in unshifted layout and ccsgn
  * as complex128 (as_c128 != 0) or complex64. */
 int fcd_get_carrier_mask(fcd_plan* plan, int carrier, uint8_t* mask_dev, void* stream);

@@ -29,10 +29,15 @@ def reference_available() -> bool:
 
 
 class _Region:
+    """The regionprops attributes the reference reads (label, coords, area, bbox, centroid)."""
+
     def __init__(self, lab, l):
         self.label = l
         self.coords = np.argwhere(lab == l)
         self.area = len(self.coords)
+        r, c = self.coords[:, 0], self.coords[:, 1]
+        self.bbox = (int(r.min()), int(c.min()), int(r.max()) + 1, int(c.max()) + 1)
+        self.centroid = tuple(self.coords.mean(axis=0))
 
 
 def _install_shims():
@@ -52,6 +57,12 @@ def _install_shims():
 
         measure.label = label
         measure.regionprops = regionprops
+        measure.find_contours = lambda *a, **k: []
+        sk_io = types.ModuleType("skimage.io")
+        sk_transform = types.ModuleType("skimage.transform")
+        sk_transform.warp = sk_transform.rotate = lambda *a, **k: None
+        sk.io, sk.transform = sk_io, sk_transform
+        sys.modules.update({"skimage.io": sk_io, "skimage.transform": sk_transform})
         draw = types.ModuleType("skimage.draw")
 
         def disk(center, radius, *, shape=None):
@@ -72,7 +83,25 @@ def _install_shims():
         plt.subplots = _noop
         plt.show = _noop
         mpl.pyplot = plt
-        sys.modules.update({"matplotlib": mpl, "matplotlib.pyplot": plt})
+        anim = types.ModuleType("matplotlib.animation")
+        mpl.animation = anim
+        sys.modules.update({"matplotlib": mpl, "matplotlib.pyplot": plt, "matplotlib.animation": anim})
+
+
+class _reference_path:
+    """sys.path with the reference root first and WITHOUT any directory that holds this repo's
+    drop-in packages: the reference's pyfcd/ and pydata/ have no __init__.py (namespace packages),
+    so a regular package of the same name anywhere on sys.path would win over them."""
+
+    def __enter__(self):
+        self.saved = list(sys.path)
+        keep = [p for p in sys.path if not os.path.exists(os.path.join(p or ".", "pyfcd", "__init__.py"))]
+        sys.path[:] = [REFERENCE_ROOT] + keep
+        importlib.invalidate_caches()
+
+    def __exit__(self, *exc):
+        sys.path[:] = self.saved
+        importlib.invalidate_caches()
 
 
 def import_reference():
@@ -84,15 +113,35 @@ def import_reference():
     saved = {k: v for k, v in sys.modules.items() if k == "pyfcd" or k.startswith("pyfcd.")}
     for k in saved:
         del sys.modules[k]
-    sys.path.insert(0, REFERENCE_ROOT)
     try:
-        m_fcd = importlib.import_module("pyfcd.fcd")
-        m_four = importlib.import_module("pyfcd.fourier")
-        m_car = importlib.import_module("pyfcd.carriers")
+        with _reference_path():
+            m_fcd = importlib.import_module("pyfcd.fcd")
+            m_four = importlib.import_module("pyfcd.fourier")
+            m_car = importlib.import_module("pyfcd.carriers")
+        assert m_fcd.__file__.startswith(REFERENCE_ROOT), m_fcd.__file__
         ref = (m_fcd.fcd, m_four.fourier, m_car.Carrier)
     finally:
-        sys.path.remove(REFERENCE_ROOT)
         for k in [k for k in sys.modules if k == "pyfcd" or k.startswith("pyfcd.")]:
             del sys.modules[k]
         sys.modules.update(saved)
     return ref
+
+
+def import_reference_analyze():
+    """The unmodified reference class ``pydata.analyze.analyze`` (for analyze.mask / analyze.center)."""
+    if not reference_available():
+        raise RuntimeError("reference tree not present")
+    _install_shims()
+    saved = {k: v for k, v in sys.modules.items() if k.split(".")[0] in ("pyfcd", "pydata")}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        with _reference_path():
+            mod = importlib.import_module("pydata.analyze")
+        assert mod.__file__.startswith(REFERENCE_ROOT), mod.__file__
+        cls = mod.analyze
+    finally:
+        for k in [k for k in sys.modules if k.split(".")[0] in ("pyfcd", "pydata")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    return cls

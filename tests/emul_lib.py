@@ -115,6 +115,22 @@ class EmulPlan:
         _native.check(self.lib, self.lib.fcd_count_residues(self.h, _p(ph), n, out, None))
         return [out[i] for i in range(n)]
 
+    def structure_mask(self, frames, smoothed=14):
+        fr = np.ascontiguousarray(frames, dtype=np.float32)
+        if fr.ndim == 2:
+            fr = fr[None]
+        out = np.zeros(fr.shape, np.uint8)
+        _native.check(self.lib, self.lib.fcd_structure_mask(self.h, _p(fr), fr.shape[0], int(smoothed), _p(out), None))
+        return out.astype(bool)
+
+    def mask_center(self, masks):
+        mk = np.ascontiguousarray(masks, dtype=np.uint8)
+        if mk.ndim == 2:
+            mk = mk[None]
+        out = (ctypes.c_int * (2 * mk.shape[0]))()
+        _native.check(self.lib, self.lib.fcd_mask_center(self.h, _p(mk), mk.shape[0], out, None))
+        return [(out[2 * i], out[2 * i + 1]) for i in range(mk.shape[0])]
+
     def mask(self, i):
         m = np.zeros(self.shape, np.uint8)
         _native.check(self.lib, self.lib.fcd_get_carrier_mask(self.h, i, _p(m), None))

@@ -270,3 +270,34 @@ def test_integer_frames_residues_and_reference_cache(api, golden):
     assert np.allclose(b, a / 0.5, rtol=1e-6, atol=1e-9)
     c, _, _ = fcd.compute_height_map(g("ref") * 0.5, g("frame") * 0.5, sq, height=1.0)   # different reference -> re-bind
     assert rel_l2(c, a) < 1e-5
+
+
+def test_structure_mask_and_center_bit_exact(api):
+    """analyze.mask / analyze.center on the device: byte / integer results."""
+    import os
+    from oracle import mask_oracle as mo
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_mask.npz"))
+    sys_path_has_pydata = __import__("pydata.analyze", fromlist=["analyze"]).analyze
+    for i in range(4):
+        shape = tuple(int(v) for v in g[f"case{i}.shape"])
+        img = mo.synthetic_structure(shape, int(g[f"case{i}.seed"]))
+        smoothed = int(g[f"case{i}.smoothed"])
+        m_gold = np.unpackbits(g[f"case{i}.mask"])[: shape[0] * shape[1]].reshape(shape).astype(bool)
+        plan = api["eng"].HeightMapPlan(shape, 1)
+        flipped = np.ascontiguousarray(img[::-1, ::-1])
+        m = plan.structure_mask(np.stack([img, flipped, img, img, flipped]), smoothed)
+        assert np.array_equal(m[0].cpu().numpy(), m_gold) and np.array_equal(m[3].cpu().numpy(), m_gold)
+        assert np.array_equal(m[4].cpu().numpy(), mo.mask(flipped, smoothed))
+        c = plan.mask_center(m)
+        assert c[0] == tuple(int(v) for v in g[f"case{i}.center"]) and c[1] == mo.center(m[1].cpu().numpy())
+        plan.close()
+        mm, cc = sys_path_has_pydata.mask(img, smoothed=smoothed, find_center=True)      # drop-in classmethods
+        assert np.array_equal(mm, m_gold) and cc == c[0]
+    big = mo.synthetic_structure((2048, 2048), 11)
+    plan = api["eng"].HeightMapPlan((2048, 2048), 1)
+    m = plan.structure_mask(big, 15)
+    assert np.array_equal(m.cpu().numpy(), mo.mask(big, 15))
+    assert plan.mask_center(m)[0] == mo.center(m.cpu().numpy())
+    plan.close()
+    with pytest.raises(UnboundLocalError):
+        sys_path_has_pydata.center(np.ones((64, 64), bool))

@@ -1,0 +1,80 @@
+"""CPU: analyze.mask / analyze.center -- oracle vs reference-derived goldens, and the CUDA kernels
+in CPU emulation vs both (bit-exact: these are byte / integer results)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import mask_oracle as mo
+from tests.emul_lib import EmulPlan
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_PICS = "/root/reference/examples/Pictures"
+
+
+@pytest.fixture(scope="module")
+def gmask():
+    return np.load(os.path.join(ROOT, "tests", "golden", "golden_mask.npz"))
+
+
+def case(g, i):
+    shape = tuple(int(v) for v in g[f"case{i}.shape"])
+    img = mo.synthetic_structure(shape, int(g[f"case{i}.seed"]))
+    m = np.unpackbits(g[f"case{i}.mask"])[: shape[0] * shape[1]].reshape(shape).astype(bool)
+    return img, int(g[f"case{i}.smoothed"]), m, tuple(int(v) for v in g[f"case{i}.center"])
+
+
+@pytest.mark.parametrize("i", [0, 1, 2, 3])
+def test_oracle_matches_reference_golden(gmask, i):
+    img, smoothed, m, c = case(gmask, i)
+    assert np.array_equal(mo.mask(img, smoothed), m)
+    assert mo.center(m) == c
+
+
+@pytest.mark.parametrize("i", [0, 1, 2, 3])
+def test_emulated_kernels_bit_exact(gmask, i):
+    img, smoothed, m, c = case(gmask, i)
+    plan = EmulPlan(img.shape)
+    flipped = np.ascontiguousarray(img[::-1, ::-1])
+    got = plan.structure_mask(np.stack([img, flipped, img, img, flipped]), smoothed)     # two chunks of the kernel batch
+    assert np.array_equal(got[0], m) and np.array_equal(got[2], m) and np.array_equal(got[3], m)
+    assert np.array_equal(got[1], mo.mask(flipped, smoothed)) and np.array_equal(got[4], got[1])
+    centers = plan.mask_center(got)
+    assert centers[0] == c and centers[2] == c and centers[1] == mo.center(got[1])
+    plan.close()
+
+
+def test_degenerate_masks():
+    plan = EmulPlan((64, 64))
+    full = np.ones((64, 64), bool)
+    ring = np.zeros((64, 64), bool); ring[10:50, 10:50] = True; ring[20:40, 22:44] = False
+    touching = np.zeros((64, 64), bool); touching[0:30, 5:40] = True      # ~mask is one region that touches the border
+    two = ring.copy(); two[12:16, 12:16] = False                           # a second, smaller hole
+    got = plan.mask_center(np.stack([full, ring, touching, two]))
+    assert got[0] == (-1, -1) and got[2] == (-1, -1)
+    assert got[1] == mo.center(ring) == (29, 32)
+    assert got[3] == mo.center(two) == (29, 32)
+    with pytest.raises(UnboundLocalError):
+        mo.center(full)
+    img = np.full((64, 64), 7.0, np.float32)                               # nothing below the mean -> empty mask
+    assert not plan.structure_mask(img, 5).any()
+    plan.close()
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_PICS), reason="reference fixtures not on this machine")
+def test_real_fixture_against_the_reference_itself():
+    """examples/mask_example.py: frame 6 of the mask series, smoothed=15, through the unmodified
+    reference class, the oracle and the emulated kernels."""
+    import cv2
+    from oracle.ref_shims import import_reference_analyze
+    analyze = import_reference_analyze()
+    path = os.path.join(REF_PICS, "mask", "0_5mm_circular_100ms_20250529_141304_C1S0001000006.tif")
+    img = cv2.imread(path, cv2.IMREAD_UNCHANGED).astype(np.float32)
+    m_ref = analyze.mask(img, smoothed=15)
+    c_ref = analyze.center(m_ref)
+    assert np.array_equal(mo.mask(img, 15), m_ref) and mo.center(m_ref) == tuple(c_ref)
+    plan = EmulPlan(img.shape)
+    m = plan.structure_mask(img, 15)[0]
+    assert np.array_equal(m, m_ref)
+    assert plan.mask_center(m)[0] == tuple(c_ref)
+    plan.close()

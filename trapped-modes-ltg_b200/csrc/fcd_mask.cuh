@@ -1,0 +1,337 @@
+// fcd_mask.cuh -- floating-structure mask and cavity centre on the device.
+//
+// Reference: analyze.mask (pydata/analyze.py:43-100) and analyze.center (pydata/analyze.py:104-140):
+//   smooth = scipy.ndimage.uniform_filter(image, size); Mask = smooth < np.mean(smooth);
+//   mask = largest 8-connected region of Mask;  centre = int(centroid) of the largest 8-connected
+//   region of ~mask whose bounding box does not touch the border.
+// These are byte / integer results, so the arithmetic in front of the threshold is reproduced
+// bit for bit:
+//   * uniform_filter (scipy 1.18): per line a float64 running sum `tmp += new - old`, output
+//     (float)(tmp / size), axis 0 first then axis 1, 'reflect' boundary, window [-(size/2), size-size/2-1];
+//   * np.mean of a float32 array: pairwise summation in float32 -- 128-element blocks with eight
+//     interleaved accumulators, then a binary tree (exact for the power-of-two sizes supported).
+// Connected components: lock-free union-find on pixel indices; the root of a component is its
+// smallest raster index, so "first label" ties resolve like skimage.measure.label.
+#pragma once
+#include "fcd_generic.cuh"
+
+namespace fcd {
+
+struct ElemBase : NoPrologue {
+    static constexpr bool BLOCKED_TILES = false;
+    static constexpr bool PIPELINED = false;
+    static constexpr int SYNC_THREADS = 0;
+    static constexpr int MIN_BLOCKS = 1;
+    static constexpr int THREADS = 256, PHASES = 1, SMEM_BYTES = 16;
+    struct State { int dummy; };
+};
+
+// ---- box filter along one axis: one thread per line ---------------------------------------
+struct BoxLinesParams {
+    const float* in;
+    float* out;
+    int H, W, size, axis;
+    long long n_lines;        // frames * (axis == 0 ? W : H)
+};
+struct BoxLines : ElemBase {
+    using Params = BoxLinesParams;
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
+        const long long line = (long long)bx * THREADS + tid;
+        if (line >= p.n_lines) return;
+        const int per = p.axis == 0 ? p.W : p.H;
+        const long long frame = line / per;
+        const int pos = (int)(line % per);
+        const int n = p.axis == 0 ? p.H : p.W;
+        const long long stride = p.axis == 0 ? p.W : 1;
+        const long long base = frame * p.H * p.W + (p.axis == 0 ? pos : (long long)pos * p.W);
+        const float* __restrict__ a = p.in + base;
+        float* __restrict__ o = p.out + base;
+        const int s1 = p.size / 2, s2 = p.size - s1 - 1;
+        const double dsize = (double)p.size;
+        auto at = [&](int j) -> double {           // 'reflect': d c b a | a b c d | d c b a
+            if (j < 0) j = -j - 1;
+            if (j >= n) j = 2 * n - 1 - j;
+            return (double)a[(long long)j * stride];
+        };
+        double tmp = 0.0;
+        for (int l = 0; l < p.size; ++l) tmp += at(l - s1);
+        o[0] = (float)(tmp / dsize);
+        for (int l = 1; l < n; ++l) {
+            const double d = at(l + s2) - at(l - 1 - s1);
+            tmp += d;
+            o[(long long)l * stride] = (float)(tmp / dsize);
+        }
+    }
+};
+
+// ---- np.mean(float32): block sums of 128 with eight accumulators, then a binary tree ------
+FCD_HD float fadd_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fadd_rn(a, b);
+#else
+    volatile float r = a + b;
+    return r;
+#endif
+}
+struct PairBlockParams {
+    const float* in;     // [frames][n]
+    float* out;          // [frames][n / 128]
+    long long n_blocks;  // frames * n / 128
+};
+struct PairBlockSum : ElemBase {
+    using Params = PairBlockParams;
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
+        const long long b = (long long)bx * THREADS + tid;
+        if (b >= p.n_blocks) return;
+        const float* __restrict__ a = p.in + b * 128;
+        float r[8];
+        for (int k = 0; k < 8; ++k) r[k] = a[k];
+        for (int i = 8; i < 128; i += 8)
+            for (int k = 0; k < 8; ++k) r[k] = fadd_rn(r[k], a[i + k]);
+        p.out[b] = fadd_rn(fadd_rn(fadd_rn(r[0], r[1]), fadd_rn(r[2], r[3])),
+                           fadd_rn(fadd_rn(r[4], r[5]), fadd_rn(r[6], r[7])));
+    }
+};
+struct PairTreeParams {
+    const float* in;     // [frames][2 * n_out]
+    float* out;          // [frames][n_out]
+    long long total;     // frames * n_out
+};
+struct PairTree : ElemBase {
+    using Params = PairTreeParams;
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
+        const long long i = (long long)bx * THREADS + tid;
+        if (i < p.total) p.out[i] = fadd_rn(p.in[2 * i], p.in[2 * i + 1]);
+    }
+};
+
+// ---- connected components -------------------------------------------------------------------
+FCD_HD int uf_find(const int* L, int i) {
+    int r = L[i];
+    while (r != i) { i = r; r = L[i]; }
+    return r;
+}
+FCD_HD void uf_unite(int* L, int a, int b) {
+    for (;;) {
+        a = uf_find(L, a);
+        b = uf_find(L, b);
+        if (a == b) return;
+        if (a > b) { const int t = a; a = b; b = t; }      // a < b: hang b under a
+#if defined(__CUDA_ARCH__)
+        const int old = atomicMin(&L[b], a);
+#else
+        const int old = L[b];
+        if (a < old) L[b] = a;
+#endif
+        if (old == b) return;
+        b = old;
+    }
+}
+
+struct LabelInitParams {
+    const float* smooth;      // mode 0: foreground = smooth < sum[frame] / n
+    const float* sums;        // [frames] pairwise float32 sums
+    const uint8_t* mask;      // mode 1: foreground = !mask
+    int* L;                   // [frames][n]  pixel index within the frame, or -1
+    long long total;
+    int n;                    // pixels per frame
+    int mode;
+};
+struct LabelInit : ElemBase {
+    using Params = LabelInitParams;
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
+        const long long i = (long long)bx * THREADS + tid;
+        if (i >= p.total) return;
+        const long long f = i / p.n;
+        const int px = (int)(i % p.n);
+        bool fg;
+        if (p.mode == 0) {
+            const float thr = p.sums[f] / (float)p.n;       // np.mean: float32 sum / count in float32
+            fg = p.smooth[i] < thr;
+        } else {
+            fg = p.mask[i] == 0;
+        }
+        p.L[i] = fg ? px : -1;
+    }
+};
+struct LabelMergeParams {
+    int* L;
+    long long total;
+    int H, W;
+};
+struct LabelMerge : ElemBase {
+    using Params = LabelMergeParams;
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
+        const long long i = (long long)bx * THREADS + tid;
+        if (i >= p.total) return;
+        const int n = p.H * p.W;
+        int* L = p.L + (i / n) * n;
+        const int px = (int)(i % n);
+        if (L[px] < 0) return;
+        const int r = px / p.W, c = px % p.W;
+        if (c > 0 && L[px - 1] >= 0) uf_unite(L, px, px - 1);                               // W
+        if (r > 0) {
+            if (L[px - p.W] >= 0) uf_unite(L, px, px - p.W);                                 // N
+            if (c > 0 && L[px - p.W - 1] >= 0) uf_unite(L, px, px - p.W - 1);               // NW
+            if (c + 1 < p.W && L[px - p.W + 1] >= 0) uf_unite(L, px, px - p.W + 1);         // NE
+        }
+    }
+};
+
+FCD_HD void atomic_add_i32(int* a, int v) {
+#if defined(__CUDA_ARCH__)
+    atomicAdd(a, v);
+#else
+    *a += v;
+#endif
+}
+FCD_HD void atomic_min_i32(int* a, int v) {
+#if defined(__CUDA_ARCH__)
+    atomicMin(a, v);
+#else
+    if (v < *a) *a = v;
+#endif
+}
+FCD_HD void atomic_max_i32(int* a, int v) {
+#if defined(__CUDA_ARCH__)
+    atomicMax(a, v);
+#else
+    if (v > *a) *a = v;
+#endif
+}
+FCD_HD void atomic_add_u64(unsigned long long* a, unsigned long long v) {
+#if defined(__CUDA_ARCH__)
+    atomicAdd(a, v);
+#else
+    *a += v;
+#endif
+}
+
+// per-root statistics (arrays indexed by the root's pixel index, per frame)
+struct RegionStats {
+    int* area;                      // zero-initialised
+    int* minr; int* maxr; int* minc; int* maxc;     // initialised to +big / -1 (only with bbox)
+    unsigned long long* sumr; unsigned long long* sumc;
+};
+struct LabelFlattenParams {
+    int* L;
+    RegionStats st;
+    long long total;
+    int H, W;
+    int with_bbox;
+};
+struct LabelFlatten : ElemBase {
+    using Params = LabelFlattenParams;
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
+        const long long i = (long long)bx * THREADS + tid;
+        if (i >= p.total) return;
+        const int n = p.H * p.W;
+        const long long fo = (i / n) * n;
+        int* L = p.L + fo;
+        const int px = (int)(i % n);
+        if (L[px] < 0) return;
+        const int root = uf_find(L, px);
+        L[px] = root;        // roots keep pointing at themselves, so concurrent finds stay valid
+        atomic_add_i32(p.st.area + fo + root, 1);
+        if (p.with_bbox) {
+            const int r = px / p.W, c = px % p.W;
+            atomic_min_i32(p.st.minr + fo + root, r);
+            atomic_max_i32(p.st.maxr + fo + root, r);
+            atomic_min_i32(p.st.minc + fo + root, c);
+            atomic_max_i32(p.st.maxc + fo + root, c);
+            atomic_add_u64(p.st.sumr + fo + root, (unsigned long long)r);
+            atomic_add_u64(p.st.sumc + fo + root, (unsigned long long)c);
+        }
+    }
+};
+
+// largest region per frame: key = area << 32 | ~root  (ties -> smallest root = first label)
+struct LargestParams {
+    const int* L;
+    RegionStats st;
+    unsigned long long* best;     // [frames], zero-initialised
+    long long total;
+    int H, W;
+    int holes_only;               // keep regions whose bounding box stays off the border
+};
+struct LargestRegion : ElemBase {
+    using Params = LargestParams;
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
+        const long long i = (long long)bx * THREADS + tid;
+        if (i >= p.total) return;
+        const int n = p.H * p.W;
+        const long long f = i / n, fo = f * n;
+        const int px = (int)(i % n);
+        if (p.L[i] != px) return;                       // not a root
+        if (p.holes_only) {
+            const bool inside = p.st.minr[fo + px] > 0 && p.st.minc[fo + px] > 0 &&
+                                p.st.maxr[fo + px] + 1 < p.H && p.st.maxc[fo + px] + 1 < p.W;
+            if (!inside) return;
+        }
+        const unsigned long long key = ((unsigned long long)(unsigned)p.st.area[fo + px] << 32) |
+                                       (unsigned long long)(0xFFFFFFFFu - (unsigned)px);
+        atomic_max_u64(p.best + f, key);
+    }
+};
+
+struct MaskOutParams {
+    const int* L;
+    const unsigned long long* best;
+    uint8_t* mask;
+    long long total;
+    int n;
+};
+struct MaskOut : ElemBase {
+    using Params = MaskOutParams;
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
+        const long long i = (long long)bx * THREADS + tid;
+        if (i >= p.total) return;
+        const unsigned long long key = p.best[i / p.n];
+        const int root = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+        p.mask[i] = (key != 0ull && p.L[i] == root) ? 1 : 0;
+    }
+};
+
+struct CenterOutParams {
+    const unsigned long long* best;
+    RegionStats st;
+    int* centers;        // [frames][2] = (cy, cx) or (-1, -1)
+    int frames;
+    int n;
+};
+struct CenterOut : ElemBase {
+    using Params = CenterOutParams;
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
+        const int f = bx * THREADS + tid;
+        if (f >= p.frames) return;
+        const unsigned long long key = p.best[f];
+        if (key == 0ull) { p.centers[2 * f] = -1; p.centers[2 * f + 1] = -1; return; }
+        const int root = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+        const long long o = (long long)f * p.n + root;
+        const double area = (double)p.st.area[o];
+        // regionprops centroid = mean of the integer coordinates (exact sums), then int()
+        p.centers[2 * f] = (int)((double)p.st.sumr[o] / area);
+        p.centers[2 * f + 1] = (int)((double)p.st.sumc[o] / area);
+    }
+};
+
+struct FillI32Params { int* a; int v; long long total; };
+struct FillI32 : ElemBase {
+    using Params = FillI32Params;
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
+        const long long i = (long long)bx * THREADS + tid;
+        if (i < p.total) p.a[i] = p.v;
+    }
+};
+
+}  // namespace fcd

@@ -10,6 +10,7 @@
 
 #include "fcd_b200.h"
 #include "fcd_generic.cuh"
+#include "fcd_mask.cuh"
 #include "fcd_launch.cuh"
 
 namespace fcd {
@@ -438,6 +439,87 @@ struct PlanImpl {
         }
     }
 
+    // ------------------------------------------------------------------ structure mask / centre ----
+    // analyze.mask (pydata/analyze.py:43-100) and analyze.center (pydata/analyze.py:104-140)
+    static constexpr int kMaskChunk = 4;
+    rt::DevBuf<float> m_t0, m_smooth, m_ps0, m_ps1;
+    rt::DevBuf<int> m_L, m_area, m_bbox, m_centers;
+    rt::DevBuf<unsigned long long> m_sums, m_best;
+
+    static int blocks_for(long long total) { return (int)((total + 255) / 256); }
+
+    void mask_workspace(bool with_stats) {
+        const size_t n = (size_t)H * W, c = kMaskChunk;
+        m_L.alloc(c * n);
+        m_area.alloc(c * n);
+        m_best.alloc(c);
+        if (with_stats) {
+            m_bbox.alloc(4 * c * n);
+            m_sums.alloc(2 * c * n);
+            m_centers.alloc(2 * c);
+        } else {
+            m_t0.alloc(c * n);
+            m_smooth.alloc(c * n);
+            m_ps0.alloc(c * n / 128);
+            m_ps1.alloc(c * n / 256 + 1);
+        }
+    }
+
+    void structure_mask(const float* frames, int n_frames, int smoothed, uint8_t* mask_out, rt::stream_t s) {
+        if (smoothed < 1 || smoothed > std::min(H, W)) rt::fail("smoothed must be in [1, min(rows, cols)]");
+        mask_workspace(false);
+        const long long n = (long long)H * W;
+        for (int f0 = 0; f0 < n_frames; f0 += kMaskChunk) {
+            const int nf = std::min(kMaskChunk, n_frames - f0);
+            const long long total = nf * n;
+            const float* in = frames + f0 * n;
+            launch<BoxLines>(blocks_for((long long)nf * W), 1, s, BoxLinesParams{in, m_t0.ptr, H, W, smoothed, 0, (long long)nf * W});
+            launch<BoxLines>(blocks_for((long long)nf * H), 1, s, BoxLinesParams{m_t0.ptr, m_smooth.ptr, H, W, smoothed, 1, (long long)nf * H});
+            // np.mean(smooth): float32 pairwise sum
+            long long m = n / 128;
+            launch<PairBlockSum>(blocks_for(nf * m), 1, s, PairBlockParams{m_smooth.ptr, m_ps0.ptr, nf * m});
+            float* a = m_ps0.ptr;
+            float* b = m_ps1.ptr;
+            while (m > 1) {
+                m /= 2;
+                launch<PairTree>(blocks_for(nf * m), 1, s, PairTreeParams{a, b, nf * m});
+                std::swap(a, b);
+            }
+            launch<LabelInit>(blocks_for(total), 1, s, LabelInitParams{m_smooth.ptr, a, nullptr, m_L.ptr, total, (int)n, 0});
+            launch<LabelMerge>(blocks_for(total), 1, s, LabelMergeParams{m_L.ptr, total, H, W});
+            rt::dmemset(m_area.ptr, 0, sizeof(int) * (size_t)total, s);
+            rt::dmemset(m_best.ptr, 0, sizeof(unsigned long long) * (size_t)nf, s);
+            RegionStats st{m_area.ptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+            launch<LabelFlatten>(blocks_for(total), 1, s, LabelFlattenParams{m_L.ptr, st, total, H, W, 0});
+            launch<LargestRegion>(blocks_for(total), 1, s, LargestParams{m_L.ptr, st, m_best.ptr, total, H, W, 0});
+            launch<MaskOut>(blocks_for(total), 1, s, MaskOutParams{m_L.ptr, m_best.ptr, mask_out + f0 * n, total, (int)n});
+        }
+    }
+
+    void mask_center(const uint8_t* mask, int n_frames, int* centers_host, rt::stream_t s) {
+        mask_workspace(true);
+        const long long n = (long long)H * W;
+        for (int f0 = 0; f0 < n_frames; f0 += kMaskChunk) {
+            const int nf = std::min(kMaskChunk, n_frames - f0);
+            const long long total = nf * n;
+            launch<LabelInit>(blocks_for(total), 1, s, LabelInitParams{nullptr, nullptr, mask + f0 * n, m_L.ptr, total, (int)n, 1});
+            launch<LabelMerge>(blocks_for(total), 1, s, LabelMergeParams{m_L.ptr, total, H, W});
+            rt::dmemset(m_area.ptr, 0, sizeof(int) * (size_t)total, s);
+            rt::dmemset(m_sums.ptr, 0, sizeof(unsigned long long) * 2 * (size_t)total, s);
+            rt::dmemset(m_best.ptr, 0, sizeof(unsigned long long) * (size_t)nf, s);
+            int* minr = m_bbox.ptr; int* maxr = minr + total; int* minc = maxr + total; int* maxc = minc + total;
+            launch<FillI32>(blocks_for(total), 1, s, FillI32Params{minr, 0x7fffffff, total});
+            launch<FillI32>(blocks_for(total), 1, s, FillI32Params{minc, 0x7fffffff, total});
+            launch<FillI32>(blocks_for(total), 1, s, FillI32Params{maxr, -1, total});
+            launch<FillI32>(blocks_for(total), 1, s, FillI32Params{maxc, -1, total});
+            RegionStats st{m_area.ptr, minr, maxr, minc, maxc, m_sums.ptr, m_sums.ptr + total};
+            launch<LabelFlatten>(blocks_for(total), 1, s, LabelFlattenParams{m_L.ptr, st, total, H, W, 1});
+            launch<LargestRegion>(blocks_for(total), 1, s, LargestParams{m_L.ptr, st, m_best.ptr, total, H, W, 1});
+            launch<CenterOut>(blocks_for(nf), 1, s, CenterOutParams{m_best.ptr, st, m_centers.ptr, nf, (int)n});
+            rt::d2h(centers_host + 2 * f0, m_centers.ptr, sizeof(int) * 2 * (size_t)nf, s);
+        }
+    }
+
     // float32 copy of the reference for mask substitution (analyze.py:231), made on demand
     rt::DevBuf<float> ref_f32;
     bool ref_f32_valid = false;
@@ -624,6 +706,17 @@ int fcd_set_profiling(fcd_plan* plan, int enable) {
 int fcd_stage_times(fcd_plan* plan, double ms_out[7], long long launches_out[7], long long frames_out[7]) {
     if (!plan || !ms_out || !launches_out || !frames_out) { g_fcd_error = "null argument"; return FCD_ERR_INVALID; }
     return fcd_guard([&] { plan->impl.timer.collect(ms_out, launches_out, frames_out); });
+}
+
+int fcd_structure_mask(fcd_plan* plan, const float* frames_dev, int n_frames, int smoothed, uint8_t* mask_dev,
+                       void* stream) {
+    if (!plan || n_frames < 0 || (n_frames > 0 && (!frames_dev || !mask_dev))) { g_fcd_error = "bad argument"; return FCD_ERR_INVALID; }
+    return fcd_guard([&] { plan->impl.structure_mask(frames_dev, n_frames, smoothed, mask_dev, stream); });
+}
+
+int fcd_mask_center(fcd_plan* plan, const uint8_t* mask_dev, int n_frames, int* centers_out, void* stream) {
+    if (!plan || n_frames < 0 || (n_frames > 0 && (!mask_dev || !centers_out))) { g_fcd_error = "bad argument"; return FCD_ERR_INVALID; }
+    return fcd_guard([&] { plan->impl.mask_center(mask_dev, n_frames, centers_out, stream); });
 }
 
 long long fcd_launch_count(const fcd_plan* plan) { return plan ? plan->impl.launches : 0; }

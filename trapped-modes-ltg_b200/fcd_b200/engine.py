@@ -279,6 +279,32 @@ class HeightMapPlan:
             check(self.lib, self.lib.fcd_count_residues(self._h, _ptr(ph), int(n), out, _stream_ptr()))
         return [out[i] for i in range(n)]
 
+    # ---- floating-structure mask / cavity centre (pydata/analyze.py:43-140) ---------------------
+    def structure_mask(self, frames, smoothed: int = 14) -> torch.Tensor:
+        """analyze.mask for a batch: frames [n,H,W] (or [H,W]) float32 -> bool masks, bit-exact."""
+        fr = to_device_image(frames, self.device, allow_f64=False)
+        squeeze = fr.dim() == 2
+        fr = (fr.unsqueeze(0) if squeeze else fr).contiguous()
+        self._check_image(fr)
+        out = torch.empty(fr.shape, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib, self.lib.fcd_structure_mask(self._h, _ptr(fr), int(fr.shape[0]), int(smoothed), _ptr(out),
+                                                        _stream_ptr()))
+        out = out.bool()
+        return out[0] if squeeze else out
+
+    def mask_center(self, masks) -> list:
+        """analyze.center for a batch of masks: [(cy, cx), ...]; (-1, -1) where there is no enclosed region."""
+        mk = masks if isinstance(masks, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(masks))
+        mk = mk.to(self.device).to(torch.uint8)
+        mk = (mk.unsqueeze(0) if mk.dim() == 2 else mk).contiguous()
+        self._check_image(mk)
+        n = int(mk.shape[0])
+        out = (ctypes.c_int * (2 * max(n, 1)))()
+        with torch.cuda.device(self.device):
+            check(self.lib, self.lib.fcd_mask_center(self._h, _ptr(mk), n, out, _stream_ptr()))
+        return [(out[2 * i], out[2 * i + 1]) for i in range(n)]
+
     STAGES = ("row_fwd", "col_band", "row_demod", "row_link", "phase_fix", "col_integrate", "row_inv")
 
     def set_profiling(self, enable: bool) -> None:
