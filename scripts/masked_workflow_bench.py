@@ -1,0 +1,42 @@
+"""Config 5 (masked workflow, pydata/analyze.py:225-255): per frame mask -> center -> frame := where(mask, ref, frame)
+-> FCD -> height *= ~mask, all on the device.  Prints stage timings and the CPU oracle time of mask+center."""
+import os, sys, time, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "trapped-modes-ltg_b200"))
+import numpy as np, torch
+from fcd_b200 import HeightMapPlan
+from oracle import fcd_oracle as o, mask_oracle as mo
+
+n, F = 2048, 32
+dev = torch.device("cuda", 0)
+ref = o.rotated_board(n)
+rng = np.random.default_rng(5)
+# frames: the board with a dark floating ring multiplied in (a structure on the surface)
+y, x = np.mgrid[0:n, 0:n].astype(np.float64)
+frames = np.empty((F, n, n), np.float32)
+for i in range(F):
+    cy, cx = n * (0.5 + rng.uniform(-0.05, 0.05)), n * (0.5 + rng.uniform(-0.05, 0.05))
+    r = np.hypot(y - cy, x - cx) / n
+    ring = (r > 0.22) & (r < 0.33)
+    _, uy, ux = o.gaussian_bump_displacement(n, (cy, cx), n / 9, 0.6)
+    fr = o.rotated_board(n, uy=uy, ux=ux).astype(np.float32)
+    fr[ring] *= 0.15
+    frames[i] = fr
+plan = HeightMapPlan((n, n), 32, dev)
+plan.bind(ref, square_size=o.board_square_size(n), height=1.0)
+d = torch.from_numpy(frames).to(dev)
+def run():
+    m = plan.structure_mask(d, 15)
+    c = plan.mask_center(m)
+    h = plan.execute(d, mask=m)
+    return m, c, h
+m, c, h = run(); torch.cuda.synchronize()
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+ev[0].record(); m = plan.structure_mask(d, 15); ev[1].record(); c = plan.mask_center(m); ev[2].record(); h = plan.execute(d, mask=m); ev[3].record()
+torch.cuda.synchronize()
+t = [ev[i].elapsed_time(ev[i + 1]) * 1e3 / F for i in range(3)]
+t0 = time.perf_counter(); mo_m = mo.mask(frames[0], 15); mo_c = mo.center(mo_m); cpu = time.perf_counter() - t0
+ok = bool(np.array_equal(m[0].cpu().numpy(), mo_m)) and c[0] == mo_c
+print(json.dumps({"size": n, "frames": F, "us_per_frame": {"structure_mask": t[0], "mask_center": t[1], "fcd_with_mask": t[2]},
+                  "frames_per_s_total": 1e6 / sum(t), "cpu_oracle_mask_center_s_per_frame": cpu, "bit_exact_vs_oracle": ok,
+                  "center0": c[0]}))

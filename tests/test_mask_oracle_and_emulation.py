@@ -78,3 +78,27 @@ def test_real_fixture_against_the_reference_itself():
     assert np.array_equal(m, m_ref)
     assert plan.mask_center(m)[0] == tuple(c_ref)
     plan.close()
+
+
+def test_random_masks_stress_connected_components():
+    """Speckle at several densities: many small regions, diagonal-only links, ties in area."""
+    rng = np.random.default_rng(42)
+    plan = EmulPlan((64, 64), 1)
+    batch, want = [], []
+    for trial in range(120):
+        dens = rng.choice([0.35, 0.5, 0.6, 0.75, 0.9])
+        m = rng.random((64, 64)) < dens
+        if trial % 3 == 0:
+            m[20:44, 20:44] = True; m[26:38, 27:39] = rng.random((12, 12)) < 0.3     # a cavity with debris
+        batch.append(m)
+        try:
+            want.append(mo.center(m))
+        except UnboundLocalError:
+            want.append((-1, -1))
+    got = plan.mask_center(np.stack(batch))
+    assert got == want
+    # largest-region selection incl. ties: feed images whose smooth field is the mask itself (size-1 filter)
+    for trial in range(40):
+        img = (rng.random((64, 64)) < rng.choice([0.4, 0.55, 0.7])).astype(np.float32)
+        assert np.array_equal(plan.structure_mask(img, 1)[0], mo.mask(img, 1))
+    plan.close()

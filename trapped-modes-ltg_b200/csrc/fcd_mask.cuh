@@ -57,7 +57,29 @@ struct BoxLines : ElemBase {
         double tmp = 0.0;
         for (int l = 0; l < p.size; ++l) tmp += at(l - s1);
         o[0] = (float)(tmp / dsize);
-        for (int l = 1; l < n; ++l) {
+        // interior: no boundary handling, loads independent of the running sum -> unrolled
+        int l = 1;
+        for (; l < n && l - 1 - s1 < 0; ++l) {
+            const double d = at(l + s2) - at(l - 1 - s1);
+            tmp += d;
+            o[(long long)l * stride] = (float)(tmp / dsize);
+        }
+        const int l_hi = n - s2;      // l + s2 < n
+        for (; l + 8 <= l_hi; l += 8) {
+            double nv[8], ov[8];
+            FCD_UNROLL
+            for (int q = 0; q < 8; ++q) {
+                nv[q] = (double)a[(long long)(l + q + s2) * stride];
+                ov[q] = (double)a[(long long)(l + q - 1 - s1) * stride];
+            }
+            FCD_UNROLL
+            for (int q = 0; q < 8; ++q) {
+                const double d = nv[q] - ov[q];
+                tmp += d;
+                o[(long long)(l + q) * stride] = (float)(tmp / dsize);
+            }
+        }
+        for (; l < n; ++l) {
             const double d = at(l + s2) - at(l - 1 - s1);
             tmp += d;
             o[(long long)l * stride] = (float)(tmp / dsize);
@@ -135,27 +157,35 @@ struct LabelInitParams {
     const float* smooth;      // mode 0: foreground = smooth < sum[frame] / n
     const float* sums;        // [frames] pairwise float32 sums
     const uint8_t* mask;      // mode 1: foreground = !mask
-    int* L;                   // [frames][n]  pixel index within the frame, or -1
-    long long total;
-    int n;                    // pixels per frame
+    int* L;                   // [frames][n]: start index of the pixel's horizontal run, or -1
+    long long n_rows;         // frames * H
+    int H, W;
     int mode;
 };
+// Run-based labelling: every foreground pixel starts out labelled with the first pixel of its
+// horizontal run, so only vertical / diagonal links between runs remain to be merged.
 struct LabelInit : ElemBase {
     using Params = LabelInitParams;
     template <int PH>
     FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
-        const long long i = (long long)bx * THREADS + tid;
-        if (i >= p.total) return;
-        const long long f = i / p.n;
-        const int px = (int)(i % p.n);
-        bool fg;
-        if (p.mode == 0) {
-            const float thr = p.sums[f] / (float)p.n;       // np.mean: float32 sum / count in float32
-            fg = p.smooth[i] < thr;
-        } else {
-            fg = p.mask[i] == 0;
+        const long long row = (long long)bx * THREADS + tid;
+        if (row >= p.n_rows) return;
+        const long long f = row / p.H;
+        const int r = (int)(row % p.H);
+        const int n = p.H * p.W;
+        const long long o = f * n + (long long)r * p.W;
+        const float thr = p.mode == 0 ? p.sums[f] / (float)n : 0.f;   // np.mean: float32 sum / count
+        int start = -1;
+        for (int c = 0; c < p.W; ++c) {
+            const bool fg = p.mode == 0 ? (p.smooth[o + c] < thr) : (p.mask[o + c] == 0);
+            if (fg) {
+                if (start < 0) start = r * p.W + c;
+                p.L[o + c] = start;
+            } else {
+                start = -1;
+                p.L[o + c] = -1;
+            }
         }
-        p.L[i] = fg ? px : -1;
     }
 };
 struct LabelMergeParams {
@@ -163,6 +193,7 @@ struct LabelMergeParams {
     long long total;
     int H, W;
 };
+// 8-connectivity links to the previous row, once per place where two runs first touch
 struct LabelMerge : ElemBase {
     using Params = LabelMergeParams;
     template <int PH>
@@ -174,11 +205,17 @@ struct LabelMerge : ElemBase {
         const int px = (int)(i % n);
         if (L[px] < 0) return;
         const int r = px / p.W, c = px % p.W;
-        if (c > 0 && L[px - 1] >= 0) uf_unite(L, px, px - 1);                               // W
-        if (r > 0) {
-            if (L[px - p.W] >= 0) uf_unite(L, px, px - p.W);                                 // N
-            if (c > 0 && L[px - p.W - 1] >= 0) uf_unite(L, px, px - p.W - 1);               // NW
-            if (c + 1 < p.W && L[px - p.W + 1] >= 0) uf_unite(L, px, px - p.W + 1);         // NE
+        if (r == 0) return;
+        const bool w = c > 0 && L[px - 1] >= 0;
+        const bool e = c + 1 < p.W && L[px + 1] >= 0;
+        const bool nn = L[px - p.W] >= 0;
+        const bool nw = c > 0 && L[px - p.W - 1] >= 0;
+        const bool ne = c + 1 < p.W && L[px - p.W + 1] >= 0;
+        if (nn) {
+            if (!w || !nw) uf_unite(L, px, px - p.W);          // first pixel of this overlap of the two runs
+        } else {
+            if (nw && !w) uf_unite(L, px, px - p.W - 1);        // diagonal touch on the left
+            if (ne && !e) uf_unite(L, px, px - p.W + 1);        // diagonal touch on the right
         }
     }
 };
@@ -221,33 +258,53 @@ struct RegionStats {
 struct LabelFlattenParams {
     int* L;
     RegionStats st;
-    long long total;
+    long long n_rows;       // frames * H
     int H, W;
     int with_bbox;
 };
 struct LabelFlatten : ElemBase {
     using Params = LabelFlattenParams;
-    template <int PH>
-    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
-        const long long i = (long long)bx * THREADS + tid;
-        if (i >= p.total) return;
-        const int n = p.H * p.W;
-        const long long fo = (i / n) * n;
-        int* L = p.L + fo;
-        const int px = (int)(i % n);
-        if (L[px] < 0) return;
-        const int root = uf_find(L, px);
-        L[px] = root;        // roots keep pointing at themselves, so concurrent finds stay valid
-        atomic_add_i32(p.st.area + fo + root, 1);
+    FCD_HD static void flush(const Params& p, long long fo, int root, int r, int cnt, int c0, int c1, long long sc) {
+        if (cnt == 0) return;
+        atomic_add_i32(p.st.area + fo + root, cnt);
         if (p.with_bbox) {
-            const int r = px / p.W, c = px % p.W;
             atomic_min_i32(p.st.minr + fo + root, r);
             atomic_max_i32(p.st.maxr + fo + root, r);
-            atomic_min_i32(p.st.minc + fo + root, c);
-            atomic_max_i32(p.st.maxc + fo + root, c);
-            atomic_add_u64(p.st.sumr + fo + root, (unsigned long long)r);
-            atomic_add_u64(p.st.sumc + fo + root, (unsigned long long)c);
+            atomic_min_i32(p.st.minc + fo + root, c0);
+            atomic_max_i32(p.st.maxc + fo + root, c1);
+            atomic_add_u64(p.st.sumr + fo + root, (unsigned long long)cnt * (unsigned long long)r);
+            atomic_add_u64(p.st.sumc + fo + root, (unsigned long long)sc);
         }
+    }
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
+        const long long row = (long long)bx * THREADS + tid;
+        if (row >= p.n_rows) return;
+        const int n = p.H * p.W;
+        const long long fo = (row / p.H) * n;
+        const int r = (int)(row % p.H);
+        int* L = p.L + fo;
+        int cur_root = -1, cnt = 0, c0 = 0, c1 = 0;
+        long long sc = 0;
+        int run_label = -2, run_root = -1;
+        for (int c = 0; c < p.W; ++c) {
+            const int px = r * p.W + c;
+            const int lab = L[px];
+            if (lab < 0) { run_label = -2; continue; }
+            if (lab != run_label) {            // a new horizontal run: one find per run
+                run_label = lab;
+                run_root = uf_find(L, px);
+            }
+            // other rows may be reading L[px] while walking to their roots: writing the root keeps
+            // every chain valid (a root points at itself)
+            L[px] = run_root;
+            if (run_root != cur_root) {
+                flush(p, fo, cur_root, r, cnt, c0, c1, sc);
+                cur_root = run_root; cnt = 0; c0 = c; sc = 0;
+            }
+            ++cnt; c1 = c; sc += c;
+        }
+        flush(p, fo, cur_root, r, cnt, c0, c1, sc);
     }
 };
 

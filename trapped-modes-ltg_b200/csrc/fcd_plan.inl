@@ -441,7 +441,7 @@ struct PlanImpl {
 
     // ------------------------------------------------------------------ structure mask / centre ----
     // analyze.mask (pydata/analyze.py:43-100) and analyze.center (pydata/analyze.py:104-140)
-    static constexpr int kMaskChunk = 4;
+    static constexpr int kMaskChunk = 16;
     rt::DevBuf<float> m_t0, m_smooth, m_ps0, m_ps1;
     rt::DevBuf<int> m_L, m_area, m_bbox, m_centers;
     rt::DevBuf<unsigned long long> m_sums, m_best;
@@ -485,12 +485,12 @@ struct PlanImpl {
                 launch<PairTree>(blocks_for(nf * m), 1, s, PairTreeParams{a, b, nf * m});
                 std::swap(a, b);
             }
-            launch<LabelInit>(blocks_for(total), 1, s, LabelInitParams{m_smooth.ptr, a, nullptr, m_L.ptr, total, (int)n, 0});
+            launch<LabelInit>(blocks_for((long long)nf * H), 1, s, LabelInitParams{m_smooth.ptr, a, nullptr, m_L.ptr, (long long)nf * H, H, W, 0});
             launch<LabelMerge>(blocks_for(total), 1, s, LabelMergeParams{m_L.ptr, total, H, W});
             rt::dmemset(m_area.ptr, 0, sizeof(int) * (size_t)total, s);
             rt::dmemset(m_best.ptr, 0, sizeof(unsigned long long) * (size_t)nf, s);
             RegionStats st{m_area.ptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-            launch<LabelFlatten>(blocks_for(total), 1, s, LabelFlattenParams{m_L.ptr, st, total, H, W, 0});
+            launch<LabelFlatten>(blocks_for((long long)nf * H), 1, s, LabelFlattenParams{m_L.ptr, st, (long long)nf * H, H, W, 0});
             launch<LargestRegion>(blocks_for(total), 1, s, LargestParams{m_L.ptr, st, m_best.ptr, total, H, W, 0});
             launch<MaskOut>(blocks_for(total), 1, s, MaskOutParams{m_L.ptr, m_best.ptr, mask_out + f0 * n, total, (int)n});
         }
@@ -502,7 +502,7 @@ struct PlanImpl {
         for (int f0 = 0; f0 < n_frames; f0 += kMaskChunk) {
             const int nf = std::min(kMaskChunk, n_frames - f0);
             const long long total = nf * n;
-            launch<LabelInit>(blocks_for(total), 1, s, LabelInitParams{nullptr, nullptr, mask + f0 * n, m_L.ptr, total, (int)n, 1});
+            launch<LabelInit>(blocks_for((long long)nf * H), 1, s, LabelInitParams{nullptr, nullptr, mask + f0 * n, m_L.ptr, (long long)nf * H, H, W, 1});
             launch<LabelMerge>(blocks_for(total), 1, s, LabelMergeParams{m_L.ptr, total, H, W});
             rt::dmemset(m_area.ptr, 0, sizeof(int) * (size_t)total, s);
             rt::dmemset(m_sums.ptr, 0, sizeof(unsigned long long) * 2 * (size_t)total, s);
@@ -513,7 +513,7 @@ struct PlanImpl {
             launch<FillI32>(blocks_for(total), 1, s, FillI32Params{maxr, -1, total});
             launch<FillI32>(blocks_for(total), 1, s, FillI32Params{maxc, -1, total});
             RegionStats st{m_area.ptr, minr, maxr, minc, maxc, m_sums.ptr, m_sums.ptr + total};
-            launch<LabelFlatten>(blocks_for(total), 1, s, LabelFlattenParams{m_L.ptr, st, total, H, W, 1});
+            launch<LabelFlatten>(blocks_for((long long)nf * H), 1, s, LabelFlattenParams{m_L.ptr, st, (long long)nf * H, H, W, 1});
             launch<LargestRegion>(blocks_for(total), 1, s, LargestParams{m_L.ptr, st, m_best.ptr, total, H, W, 1});
             launch<CenterOut>(blocks_for(nf), 1, s, CenterOutParams{m_best.ptr, st, m_centers.ptr, nf, (int)n});
             rt::d2h(centers_host + 2 * f0, m_centers.ptr, sizeof(int) * 2 * (size_t)nf, s);
