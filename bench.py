@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=3, help="frames timed for the cpu_baseline object")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--peak-px", type=float, nargs=2, default=[0.2, 0.8],
+                    help="range of the peak displacement in pixels (SURVEY 8(d): 0.2-0.8; 4-5 exercises the unwrap path)")
     ap.add_argument("--no-cufft", action="store_true", help="skip the cuFFT-based comparison pipeline")
     ap.add_argument("--cufft-frames", type=int, default=64)
     return ap.parse_args()
@@ -67,7 +69,7 @@ def measured_peak_gbs():
 # --------------------------------------------------------------------------------------
 # synthetic workload: rotated periodic board, Gaussian-bump displacement
 # --------------------------------------------------------------------------------------
-def make_frames_gpu(n, count, seed, device, chunk=8):
+def make_frames_gpu(n, count, seed, device, chunk=8, peak_range=(0.2, 0.8)):
     import torch
 
     from oracle import fcd_oracle as o  # generator parameters only (host scalars)
@@ -84,7 +86,7 @@ def make_frames_gpu(n, count, seed, device, chunk=8):
         cy = torch.tensor(rng.uniform(0.35 * n, 0.65 * n, m), device=device)[:, None, None]
         cx = torch.tensor(rng.uniform(0.35 * n, 0.65 * n, m), device=device)[:, None, None]
         sg = torch.tensor(rng.uniform(n / 12.0, n / 6.0, m), device=device)[:, None, None]
-        pk = torch.tensor(rng.uniform(0.2, 0.8, m), device=device)[:, None, None]
+        pk = torch.tensor(rng.uniform(peak_range[0], peak_range[1], m), device=device)[:, None, None]
         dy, dx = y - cy, x - cx
         g = torch.exp(-(dy * dy + dx * dx) / (2.0 * sg * sg))
         amp = pk * sg * np.exp(0.5)
@@ -240,7 +242,7 @@ def run_ours(args):
     n, F = args.size, args.frames
     P = n * n
     plan = HeightMapPlan((n, n), args.frames_per_launch, dev)
-    ref, frames = make_frames_gpu(n, F, SEED + rank, dev)
+    ref, frames = make_frames_gpu(n, F, SEED + rank, dev, peak_range=tuple(args.peak_px))
     from oracle import fcd_oracle as o
     sq = o.board_square_size(n)
     cal = plan.bind(ref, square_size=sq, height=1.0)
@@ -392,7 +394,7 @@ def run_ours(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"batch of {F} frames {n}x{n} float32 per GPU, one reference "
                                        f"(BASELINE.json configs[1])", "frames_per_gpu": F, "size": n,
-                           "frames_per_launch": args.frames_per_launch, "unwrap": True,
+                           "frames_per_launch": args.frames_per_launch, "unwrap": True, "peak_displacement_px": list(args.peak_px),
                            "l2": f"inputs {F * P * 4 / 1e9:.1f} GB per step are larger than the 126 MB L2 (no flush needed)",
                            "calibration_factor": cal, "parallelism": f"frame-sharded x{world}, no hot-path collective"},
                 "mpix_per_s": value * P / 1e6, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
