@@ -5,3 +5,6 @@
 #error "build with -DFCD_EMULATE"
 #endif
 #include "fcd_plan.inl"
+
+// emulation-only knob (not part of include/fcd_b200.h): thread order inside a phase
+extern "C" void fcd_emul_set_thread_order(int order) { fcd::rt::emu_thread_order() = order; }

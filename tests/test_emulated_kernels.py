@@ -204,3 +204,35 @@ def test_residue_guard(golden):
     got = plan.count_residues(noisy)
     assert got == [o.count_residues(noisy[0]), o.count_residues(noisy[1])] and got[0] > 1000
     plan.close()
+
+
+def test_thread_order_independence(golden):
+    """Racecheck by construction: inside a phase there is no barrier, so running the emulated
+    threads descending or odd-first must reproduce the ascending run bit for bit (pipeline with
+    unwrap path, masks, phases output; carrier search; mask/centre kernels)."""
+    from oracle import mask_oracle as mo
+    l = lib()
+    g = lambda k: golden[f"synth256_wrap.{k}"]
+    ref, frame, sq = g("ref").astype(np.float64), g("frame"), float(g("square_size"))
+    mask = np.zeros((256, 256), bool); mask[90:120, 60:200] = True
+    img = mo.synthetic_structure((256, 256), 2)
+
+    def run(order):
+        l.fcd_emul_set_thread_order(order)
+        try:
+            plan = EmulPlan((256, 256), 2)
+            peaks, radius, cal = bind_like_reference(plan, ref, sq)
+            h, ph = plan.execute(np.stack([frame, golden["synth256_small.frame"], frame]), phases=True)
+            hm = plan.execute(frame, mask=mask)
+            sm = plan.structure_mask(img, 14)
+            c = plan.mask_center(sm)
+            cc = plan.ccsgn(0, c128=False)
+            plan.close()
+            return [np.array(peaks), h, ph, hm, sm, np.array(c), cc]
+        finally:
+            l.fcd_emul_set_thread_order(0)
+
+    base = run(0)
+    for order in (1, 2):
+        for a, b in zip(base, run(order)):
+            assert np.array_equal(a, b)

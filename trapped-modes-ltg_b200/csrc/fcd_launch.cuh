@@ -37,6 +37,18 @@ inline void d2h(void* h, const void* d, size_t n, stream_t) { std::memcpy(h, d, 
 inline void d2d(void* d, const void* s, size_t n, stream_t) { std::memmove(d, s, n); }
 inline void sync(stream_t) {}
 
+// Order in which the emulated threads of a block run inside one phase: 0 ascending, 1 descending,
+// 2 odd threads first.  Within a phase there is no barrier, so a correct kernel must give
+// bit-identical results for every order; tests run all three (a poor man's racecheck --
+// compute-sanitizer is not available on the GPU pool).
+inline int& emu_thread_order() { static int order = 0; return order; }
+inline int emu_tid(int i, int n) {
+    const int o = emu_thread_order();
+    if (o == 1) return n - 1 - i;
+    if (o == 2) { const int odd = n / 2; return i < odd ? 2 * i + 1 : 2 * (i - odd); }
+    return i;
+}
+
 template <class K, int PH>
 inline void emu_phases(const typename K::Params& p, int bx, int by, unsigned char* smem, typename K::State* st) {
     std::vector<char> on(K::THREADS);     // evaluated before the phase runs, like the device does
@@ -46,8 +58,10 @@ inline void emu_phases(const typename K::Params& p, int bx, int by, unsigned cha
     const int dom = K::SYNC_THREADS == 0 ? K::THREADS : K::SYNC_THREADS;
     for (int tid = 0; tid < K::THREADS; ++tid)
         if (on[tid] != on[(tid / dom) * dom]) fail("emul: phase enable flag is not uniform over its barrier domain");
-    for (int tid = 0; tid < K::THREADS; ++tid)
+    for (int i = 0; i < K::THREADS; ++i) {
+        const int tid = emu_tid(i, K::THREADS);
         if (on[tid]) K::template phase<PH>(p, bx, by, tid, smem, st[tid]);
+    }
     if constexpr (PH + 1 < K::PHASES) emu_phases<K, PH + 1>(p, bx, by, smem, st);
 }
 
