@@ -345,28 +345,46 @@ struct RowDemod {
     using GL = GroupLayout<L, G, 2>;
     using Params = RowDemodParams;
     static constexpr bool BLOCKED_TILES = true;
-    static constexpr bool PIPELINED = false;
+    static constexpr bool PIPELINED = PRUNED;   // pruned path: next tile's band values arrive by cp.async
     static constexpr int SYNC_THREADS = (L / 16 >= 32 && G > 1 && G <= 15) ? L / 16 : 0;   // per-group named barriers
     static constexpr int MIN_BLOCKS = ((G * L / 16) <= 128 ? 4 : ((G * L / 16) <= 256 ? 2 : 1));
     static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 13;
     using TW = SmemTwiddles<FF, THREADS>;
     // per group: two exchange buffers (one per carrier; the second doubles as the jump-scan
-    // array), chunk totals, chunk offsets, flag
+    // array), chunk totals, chunk offsets, flag, and (pruned path) the staging slots of the
+    // four band values each thread feeds into the first pass: band[q][t], q = carrier*2 + butterfly
     static constexpr int AUX_INTS = 4 * TPF + 4;
-    static constexpr int GROUP_BYTES = GL::GROUP_STRIDE * (int)sizeof(cf) + AUX_INTS * (int)sizeof(int);
+    static constexpr int BAND_ELEMS = PRUNED ? 4 * TPF : 0;
+    static constexpr int GROUP_BYTES = GL::GROUP_STRIDE * (int)sizeof(cf) + AUX_INTS * (int)sizeof(int) +
+                                       BAND_ELEMS * (int)sizeof(cf);
     static constexpr int SMEM_BYTES = TW::TW_BYTES + G * GROUP_BYTES;
     FCD_HD static void prologue(const Params& p, int tid, unsigned char* smem) { TW::load(p.tw, tid, smem); }
     struct State {
         cf v[16];   // carrier 0, later (phi0, phi1)
         cf w[16];   // carrier 1
+        TileLink link;
     };
 
-    // the single non-zero input of first-pass butterfly ii of carrier i (pruned path)
-    FCD_HD static cf band_value(const Params& p, int f, int i, int y, int t, int ii) {
+    // Pruned path: first-pass butterfly ii of carrier i has a single non-zero input, band column
+    // c(t, ii, i) of the row -- independent of the tile.  Each thread stages its own four values
+    // (thread-private slots: cp.async + wait, no barrier) one tile ahead, so the DRAM round trip
+    // that used to open every tile (ncu r01_m2: 32 % of the kernel's samples, 65 % long
+    // scoreboard) overlaps the previous tile's arithmetic.
+    FCD_HD static int band_col(const Params& p, int i, int t, int ii) {
         constexpr int M1 = L / 8;
-        const cf* __restrict__ row = p.w2 + (((long long)f * 2 + i) * p.H + y) * p.ncp;
-        const int c = (t + TPF * ii - (p.kc0[i] & (L - 1))) & (M1 - 1);
-        return (c < p.nc[i]) ? row[c] : mk<float>(0.f, 0.f);
+        return (t + TPF * ii - (p.kc0[i] & (L - 1))) & (M1 - 1);
+    }
+    FCD_HD static cf* band_slots(unsigned char* gbase) {
+        return reinterpret_cast<cf*>(gbase + GL::GROUP_STRIDE * sizeof(cf) + AUX_INTS * sizeof(int));
+    }
+    FCD_HD static void stage_band(const Params& p, int f, int y, int t, cf* band) {
+        FCD_UNROLL
+        for (int q = 0; q < 4; ++q) {
+            const int i = q >> 1;
+            const int c = band_col(p, i, t, q & 1);
+            if (c < p.nc[i])
+                async_copy8(band + q * TPF + t, p.w2 + (((long long)f * 2 + i) * p.H + y) * p.ncp + c);
+        }
     }
 
     // the skip decision must be uniform over the barrier domain: one flag per group with
@@ -436,11 +454,15 @@ struct RowDemod {
             if (t == 0) *flag = 0;
             if constexpr (PRUNED) {
                 // band no wider than W/8: every radix-8 butterfly of the first pass has at most
-                // one non-zero input -> one load and a few rotations per butterfly
+                // one non-zero input -> one staged value and a few rotations per butterfly
                 constexpr int M1 = L / 8;
+                cf* band = band_slots(gbase);
+                if (st.link.first) stage_band(p, f, y, t, band);   // later tiles were staged in phase 1
+                async_wait_all();
                 cf nx[4];
                 FCD_UNROLL
-                for (int q = 0; q < 4; ++q) nx[q] = band_value(p, f, q >> 1, y, t, q & 1);   // loads first
+                for (int q = 0; q < 4; ++q)
+                    nx[q] = (band_col(p, q >> 1, t, q & 1) < p.nc[q >> 1]) ? band[q * TPF + t] : mk<float>(0.f, 0.f);
                 FCD_UNROLL
                 for (int i = 0; i < 2; ++i) {
                     const int p0 = p.kc0[i] & (W - 1);
@@ -459,6 +481,10 @@ struct RowDemod {
                 FI::stepA(st.w, t, s1);
             }
         } else if constexpr (PH == 1) {
+            if constexpr (PRUNED) {   // own slots were consumed before the barrier: stage the next tile
+                if (st.link.has_next)
+                    stage_band(p, st.link.next_bx, st.link.next_by * G + g, t, band_slots(gbase));
+            }
             FI::stepB2(st.v, st.w, t, s0, s1, tw);
         } else if constexpr (PH == 2) {
             FI::stepC(st.v, t, s0);
