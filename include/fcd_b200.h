@@ -63,7 +63,9 @@ int fcd_bind_reference(fcd_plan* plan, const void* reference_dev, int reference_
 
 /* The per-frame path: frames_dev[n][rows][cols] float32 -> height_dev[n][rows][cols] float32
  * (+ optional phases_dev[n][2][rows][cols] float32).  Replaces pyfcd/fcd.py:28-33:
- * fft2(displaced) -> compute_phases (fcd.py:104-120, incl. unwrap_phase when unwrap != 0)
+ * fft2(displaced) -> compute_phases (fcd.py:104-120, incl. unwrap_phase when unwrap != 0:
+ * 1 = row/column scan, exact where the wrapped phases have no residues and the fast path;
+ * 2 = reliability-guided like scikit-image, see fcd_unwrap_phase)
  * -> compute_displacement_field (fcd.py:123-138) -> -u/height -> integrate_in_fourier
  * (fourier.py:116-137).  Optional mask_dev (uint8, nonzero = masked): the frame is replaced
  * by the reference under the mask before the transform and the height map is zeroed under
@@ -89,6 +91,16 @@ int fcd_set_height(fcd_plan* plan, double height);
  * to zero.  The unwrapped phases equal scikit-image's unwrap_phase (pyfcd/fcd.py:119) up to a
  * global 2*pi*k only where this is zero.  counts_out: n_maps ints on the host. */
 int fcd_count_residues(fcd_plan* plan, const float* phases_dev, int n_maps, int* counts_out, void* stream);
+
+/* Reliability-guided 2-D phase unwrapping of n_maps maps (rows*cols float32 each, values in
+ * [-pi, pi]); may run in place.  Replaces skimage.restoration.unwrap_phase as called at
+ * pyfcd/fcd.py:119 (Herraez, Burton, Lalor, Gdeisat, Appl. Opt. 41, 7437 (2002)): pixel
+ * reliability from wrapped second differences, neighbour pairs merged in order of the summed
+ * reliabilities.  The merge order makes the result the integral of the wrapped differences
+ * along the minimum spanning tree of that edge weighting, which is built here with Boruvka
+ * rounds; output = input + 2*pi*integer, pixel (0, 0) keeps its value (scikit-image's result
+ * differs by one global 2*pi*k).  This is what fcd_execute runs when unwrap == 2. */
+int fcd_unwrap_phase(fcd_plan* plan, const float* wrapped_dev, int n_maps, float* unwrapped_dev, void* stream);
 
 /* Floating-structure mask of each frame: box filter of width `smoothed`, threshold at the mean of
  * the filtered image, largest 8-connected region below it.  Bit-exact replacement of

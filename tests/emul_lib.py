@@ -105,6 +105,13 @@ class EmulPlan:
                                                            stride, int(unwrap), None))
         return (out, ph) if phases else out
 
+    def unwrap_phase(self, wrapped):
+        w = np.ascontiguousarray(wrapped, dtype=np.float32)
+        n = w.size // (self.shape[0] * self.shape[1])
+        out = np.empty_like(w)
+        _native.check(self.lib, self.lib.fcd_unwrap_phase(self.h, _p(w), n, _p(out), None))
+        return out
+
     def set_height(self, height):
         _native.check(self.lib, self.lib.fcd_set_height(self.h, float(height)))
 

@@ -11,6 +11,7 @@
 #include "fcd_b200.h"
 #include "fcd_generic.cuh"
 #include "fcd_mask.cuh"
+#include "fcd_unwrap.cuh"
 #include "fcd_launch.cuh"
 
 namespace fcd {
@@ -374,6 +375,7 @@ struct PlanImpl {
     void execute(const void* frames, int frame_kind, int n_frames, float* height_out, float* phases,
                  const uint8_t* mask, long long mask_stride, int unwrap, rt::stream_t s) {
         if (frame_kind < 0 || frame_kind > 2) rt::fail("frame dtype must be 0 (float32), 1 (uint8) or 2 (uint16)");
+        if (unwrap < 0 || unwrap > 2) rt::fail("unwrap must be 0 (off), 1 (scan) or 2 (reliability-guided)");
         const size_t px = frame_kind == 0 ? 4 : (frame_kind == 1 ? 1 : 2);
         if (!bound) throw std::logic_error("fcd_execute called before fcd_bind_reference");
         if (n_frames < 0) rt::fail("negative frame count");
@@ -402,10 +404,18 @@ struct PlanImpl {
                 launch<ColBand<L, G>>(ceil_div(ncp, G), nf * 2, s, p);
             })
             if (profiling) timer.mark(s, 1);
+            // unwrap: 0 none, 1 row/column scan (exact where the wrapped phases have no residues),
+            // 2 reliability-guided (Herraez et al., what skimage.restoration.unwrap_phase implements)
+            const bool guided = unwrap == 2;
+            if (guided && !po) {
+                ph_ws.alloc((size_t)chunk * 2 * n);
+                po = ph_ws.ptr;
+            }
+            const int scan = (unwrap && !guided) ? 1 : 0;
             FCD_DISPATCH_L(W, {
                 constexpr int G = Tune<L>::GDEM;
                 RowDemodParams p{w2.ptr, theta.ptr, w3.ptr, colphase.ptr, po, tw_w_f.ptr, H, ncp,
-                                 {nc[0], nc[1]}, {c_lo[0] - W / 2, c_lo[1] - W / 2}, W / 2, unwrap ? 1 : 0};
+                                 {nc[0], nc[1]}, {c_lo[0] - W / 2, c_lo[1] - W / 2}, W / 2, scan};
                 bool pruned = false;
                 if constexpr (Plan<L>::R1 == 8) {
                     if (nc[0] <= L / 8 && nc[1] <= L / 8) {
@@ -416,17 +426,27 @@ struct PlanImpl {
                 if (!pruned) launch<RowDemod<L, G, false>>(nf, H / G, s, p);
             })
             if (profiling) timer.mark(s, 2);
-            launch<RowLink>(2, nf, s, RowLinkParams{colphase.ptr, rowoff.ptr, H, H / 2, unwrap ? 1 : 0});
-            if (profiling) timer.mark(s, 3);
-            if (po && unwrap) {
-                launch<PhaseFix>(H, nf * 2, s, PhaseFixParams{po, rowoff.ptr, H, W});
+            if (guided) {
+                unwrap_maps(po, nf * 2, po, s);                       // in place
+                if (profiling) timer.mark(s, 3);
+                FCD_DISPATCH_L(W, {
+                    constexpr int G = Tune<L>::GROW;
+                    launch<RowPhaseFwd<L, G>>(H / G, nf, s, RowPhaseFwdParams{po, w3.ptr, tw_w_f.ptr, H});
+                })
                 if (profiling) timer.mark(s, 4);
+            } else {
+                launch<RowLink>(2, nf, s, RowLinkParams{colphase.ptr, rowoff.ptr, H, H / 2, scan});
+                if (profiling) timer.mark(s, 3);
+                if (po && scan) {
+                    launch<PhaseFix>(H, nf * 2, s, PhaseFixParams{po, rowoff.ptr, H, W});
+                    if (profiling) timer.mark(s, 4);
+                }
             }
             FCD_DISPATCH_L(H, {
                 constexpr int G = Tune<L>::GCOL;
                 ColIntegrateParams p{w3.ptr, rowoff.ptr, w4.ptr, tw_h_f.ptr, kx.ptr, kxq.ptr, dky, W, w4p,
                                      (float)f[0][0], (float)f[0][1], (float)f[1][0], (float)f[1][1], scale_int,
-                                     unwrap ? 1 : 0};
+                                     scan};
                 launch<ColIntegrate<L, G>>(ceil_div(W / 2 + 1, G), nf, s, p);
             })
             if (profiling) timer.mark(s, 5);
@@ -436,6 +456,61 @@ struct PlanImpl {
                 launch<RowInv<L, G>>(H / (2 * G), nf, s, p);
             })
             if (profiling) timer.mark(s, 6);
+        }
+    }
+
+    // ------------------------------------------------------------------ reliability-guided unwrap ----
+    // skimage.restoration.unwrap_phase (pyfcd/fcd.py:119): see fcd_unwrap.cuh.  Boruvka rounds until
+    // no component has an outgoing edge left; kUnwrapMaps maps share one round (one host sync each).
+    static constexpr int kUnwrapMaps = 8;
+    rt::DevBuf<float> ph_ws;
+    rt::DevBuf<double> u_rel, u_border;
+    rt::DevBuf<po_t> u_po;
+    rt::DevBuf<unsigned long long> u_bw;
+    rt::DevBuf<unsigned> u_be;
+    rt::DevBuf<int> u_merges;
+    long long unwrap_rounds = 0;
+
+    void unwrap_maps(const float* wrapped, int n_maps, float* out, rt::stream_t s) {
+        const long long n = (long long)H * W;
+        if (u_border.count != (size_t)(2 * W + 2 * H)) {
+            // the same deterministic filler as oracle/unwrap_herraez.c (scikit-image draws these at random)
+            std::vector<double> b((size_t)(2 * W + 2 * H));
+            unsigned long long lcg = 0x9E3779B97F4A7C15ull;
+            for (long long i = 0; i < n; ++i) {
+                lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+                const int r = (int)(i / W), c = (int)(i % W);
+                if (r == 0 || c == 0 || r == H - 1 || c == W - 1) {
+                    const int bi = r == 0 ? c : (r == H - 1 ? W + c : (c == 0 ? 2 * W + r : 2 * W + H + r));
+                    b[(size_t)bi] = 9999999.0 + (double)(lcg >> 11) / 9007199254740992.0;
+                }
+            }
+            u_border.upload(b, s);
+        }
+        const size_t cap = (size_t)kUnwrapMaps * n;
+        u_rel.alloc(cap); u_po.alloc(cap); u_bw.alloc(cap); u_be.alloc(cap); u_merges.alloc(1);
+        for (int m0 = 0; m0 < n_maps; m0 += kUnwrapMaps) {
+            const int nm = std::min(kUnwrapMaps, n_maps - m0);
+            const long long total = nm * n;
+            const float* w = wrapped + m0 * n;
+            launch<MstReliability>(blocks_for(total), 1, s, MstRelParams{w, u_border.ptr, u_rel.ptr, u_po.ptr, total, H, W});
+            MstRoundParams rp{w, u_rel.ptr, u_po.ptr, u_bw.ptr, u_be.ptr, u_merges.ptr, total, H, W, nullptr};
+            MstRoundParams rp2 = rp;
+            rp2.total = 2 * total;
+            for (int round = 0; round < 64; ++round) {
+                rt::dmemset(u_merges.ptr, 0, sizeof(int), s);
+                launch<MstReset>(blocks_for(total), 1, s, rp);
+                launch<MstSelect<0>>(blocks_for(2 * total), 1, s, rp2);
+                launch<MstSelect<1>>(blocks_for(2 * total), 1, s, rp2);
+                launch<MstUnite>(blocks_for(total), 1, s, rp);
+                launch<MstFlatten>(blocks_for(total), 1, s, rp);
+                int merges = 0;
+                rt::d2h(&merges, u_merges.ptr, sizeof(int), s);
+                ++unwrap_rounds;
+                if (merges == 0) break;
+            }
+            rp.out = out + m0 * n;
+            launch<MstApply>(blocks_for(total), 1, s, rp);
         }
     }
 
@@ -706,6 +781,14 @@ int fcd_set_profiling(fcd_plan* plan, int enable) {
 int fcd_stage_times(fcd_plan* plan, double ms_out[7], long long launches_out[7], long long frames_out[7]) {
     if (!plan || !ms_out || !launches_out || !frames_out) { g_fcd_error = "null argument"; return FCD_ERR_INVALID; }
     return fcd_guard([&] { plan->impl.timer.collect(ms_out, launches_out, frames_out); });
+}
+
+int fcd_unwrap_phase(fcd_plan* plan, const float* wrapped_dev, int n_maps, float* unwrapped_dev, void* stream) {
+    if (!plan || n_maps < 0 || (n_maps > 0 && (!wrapped_dev || !unwrapped_dev))) { g_fcd_error = "bad argument"; return FCD_ERR_INVALID; }
+    return fcd_guard([&] {
+        plan->impl.unwrap_maps(wrapped_dev, n_maps, unwrapped_dev, stream);
+        fcd::rt::sync(stream);
+    });
 }
 
 int fcd_structure_mask(fcd_plan* plan, const float* frames_dev, int n_frames, int smoothed, uint8_t* mask_dev,

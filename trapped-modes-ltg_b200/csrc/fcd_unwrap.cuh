@@ -1,0 +1,283 @@
+// fcd_unwrap.cuh -- reliability-guided 2-D phase unwrapping on the device.
+//
+// Reference: skimage.restoration.unwrap_phase called at pyfcd/fcd.py:119, i.e. Herraez, Burton,
+// Lalor, Gdeisat, Appl. Opt. 41, 7437 (2002): pixel reliability from wrapped second
+// differences, edges (horizontal + vertical neighbour pairs) sorted by the sum of the two
+// reliabilities, groups merged in that order, each merge shifting one group by the integer
+// number of 2*pi that removes the jump across the edge.
+//
+// Merging in sorted order and skipping edges inside a group is Kruskal's algorithm: the
+// result is "integrate the wrapped differences along the minimum spanning tree of the
+// reliability-weighted grid graph", up to one global 2*pi*k (verified pixel for pixel against
+// oracle/unwrap_herraez.c on the reference's own example pair, 337 and 250 residues).  The MST
+// under a strict total order (weight, then edge index: horizontal edges before vertical ones,
+// raster order -- the order the sequential algorithm creates them in) is unique, so Boruvka's
+// parallel algorithm builds the same tree.  The union-find carries integer potentials:
+// word = (offset to parent) << 32 | parent, unwrapped[p] = wrapped[p] + 2*pi*pot(p).
+#pragma once
+#include "fcd_mask.cuh"
+
+namespace fcd {
+
+constexpr double kPiD = 3.14159265358979323846;
+
+FCD_HD double wrap_pi_d(double d) {
+    if (d > kPiD) return d - 2.0 * kPiD;
+    if (d < -kPiD) return d + 2.0 * kPiD;
+    return d;
+}
+// number of 2*pi to add to b so that it is within pi of a (sign convention of the oracle)
+FCD_HD int jump_between(double a, double b) {
+    const double d = a - b;
+    if (d > kPiD) return -1;
+    if (d < -kPiD) return 1;
+    return 0;
+}
+
+FCD_HD void atomic_min_u64(unsigned long long* a, unsigned long long v) {
+#if defined(__CUDA_ARCH__)
+    atomicMin(a, v);
+#else
+    if (v < *a) *a = v;
+#endif
+}
+FCD_HD void atomic_min_u32(unsigned* a, unsigned v) {
+#if defined(__CUDA_ARCH__)
+    atomicMin(a, v);
+#else
+    if (v < *a) *a = v;
+#endif
+}
+
+using po_t = unsigned long long;
+FCD_HD po_t po_pack(int parent, int off) { return ((po_t)(unsigned)off << 32) | (po_t)(unsigned)parent; }
+FCD_HD int po_parent(po_t v) { return (int)(unsigned)(v & 0xffffffffull); }
+FCD_HD int po_off(po_t v) { return (int)(unsigned)(v >> 32); }
+
+FCD_HD po_t po_load(const po_t* p) {
+#if defined(__CUDA_ARCH__)
+    return *reinterpret_cast<const volatile po_t*>(p);
+#else
+    return *p;
+#endif
+}
+// root of x and the potential of x relative to that root
+FCD_HD void pot_find(const po_t* PO, int x, int& root, int& pot) {
+    int acc = 0;
+    for (;;) {
+        const po_t v = po_load(PO + x);
+        const int par = po_parent(v);
+        if (par == x) { root = x; pot = acc; return; }
+        acc += po_off(v);
+        x = par;
+    }
+}
+// make pot(v) = pot(u) + delta by linking the two roots (larger index under smaller)
+FCD_HD bool pot_unite(po_t* PO, int u, int v, int delta) {
+    for (;;) {
+        int ru, pu, rv, pv;
+        pot_find(PO, u, ru, pu);
+        pot_find(PO, v, rv, pv);
+        if (ru == rv) return false;
+        int child, parent, off;
+        if (ru < rv) { child = rv; parent = ru; off = pu + delta - pv; }
+        else         { child = ru; parent = rv; off = pv - delta - pu; }
+        const po_t expected = po_pack(child, 0), desired = po_pack(parent, off);
+#if defined(__CUDA_ARCH__)
+        const po_t old = atomicCAS(PO + child, expected, desired);
+#else
+        const po_t old = PO[child];
+        if (old == expected) PO[child] = desired;
+#endif
+        if (old == expected) return true;
+    }
+}
+
+// edge e of a map with n = H*W pixels: e < n horizontal (p, p+1), e >= n vertical (p, p+W)
+FCD_HD bool edge_ends(int e, int n, int H, int W, int& p, int& q) {
+    if (e < n) { p = e; q = e + 1; return (e % W) != W - 1; }
+    p = e - n; q = p + W; return p / W != H - 1;
+}
+
+// ---- reliability (double) ---------------------------------------------------------------------
+struct MstRelParams {
+    const float* w;            // [maps][n] wrapped phases
+    const double* border;      // [2W + 2H] reliability of border pixels (large + deterministic filler):
+                               // top row, bottom row, left column, right column
+    double* rel;               // [maps][n]
+    po_t* PO;                  // [maps][n] initialised to (self, 0)
+    long long total;
+    int H, W;
+};
+struct MstReliability : ElemBase {
+    using Params = MstRelParams;
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
+        const long long i = (long long)bx * THREADS + tid;
+        if (i >= p.total) return;
+        const int n = p.H * p.W;
+        const int px = (int)(i % n);
+        const int r = px / p.W, c = px % p.W;
+        p.PO[i] = po_pack(px, 0);
+        if (r == 0 || c == 0 || r == p.H - 1 || c == p.W - 1) {
+            const int b = r == 0 ? c : (r == p.H - 1 ? p.W + c : (c == 0 ? 2 * p.W + r : 2 * p.W + p.H + r));
+            p.rel[i] = p.border[b];
+            return;
+        }
+        const float* w = p.w + i;
+        const int W = p.W;
+        const double c0 = (double)w[0];
+        const double h = wrap_pi_d((double)w[-1] - c0) - wrap_pi_d(c0 - (double)w[1]);
+        const double v = wrap_pi_d((double)w[-W] - c0) - wrap_pi_d(c0 - (double)w[W]);
+        const double d1 = wrap_pi_d((double)w[-W - 1] - c0) - wrap_pi_d(c0 - (double)w[W + 1]);
+        const double d2 = wrap_pi_d((double)w[-W + 1] - c0) - wrap_pi_d(c0 - (double)w[W - 1]);
+        p.rel[i] = h * h + v * v + d1 * d1 + d2 * d2;
+    }
+};
+
+// ---- one Boruvka round ---------------------------------------------------------------------------
+struct MstRoundParams {
+    const float* w;
+    const double* rel;
+    po_t* PO;
+    unsigned long long* best_w;   // [maps][n] per root: smallest outgoing weight (bit pattern of a double >= 0)
+    unsigned* best_e;             // [maps][n] per root: smallest edge index among those of that weight
+    int* merges;                  // number of successful unions in this round
+    long long total;              // maps * n (MstReset, MstUnite, MstFlatten, MstApply) or maps * 2n (select)
+    int H, W;
+    float* out;                   // MstApply
+};
+struct MstReset : ElemBase {
+    using Params = MstRoundParams;
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
+        const long long i = (long long)bx * THREADS + tid;
+        if (i >= p.total) return;
+        p.best_w[i] = ~0ull;
+        p.best_e[i] = ~0u;
+    }
+};
+template <int PASS>   // 0: minimum weight per component, 1: minimum edge index among the minimum-weight edges
+struct MstSelect : ElemBase {
+    using Params = MstRoundParams;
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
+        const long long i = (long long)bx * THREADS + tid;
+        if (i >= p.total) return;
+        const int n = p.H * p.W;
+        const long long map = i / (2LL * n);
+        const int e = (int)(i % (2LL * n));
+        int u, v;
+        if (!edge_ends(e, n, p.H, p.W, u, v)) return;
+        const po_t* PO = p.PO + map * n;
+        int ru, rv, t0, t1;
+        pot_find(PO, u, ru, t0);
+        pot_find(PO, v, rv, t1);
+        if (ru == rv) return;
+        const double* rel = p.rel + map * n;
+        const unsigned long long key = f64_bits(rel[u] + rel[v]);
+        unsigned long long* bw = p.best_w + map * n;
+        if (PASS == 0) {
+            atomic_min_u64(bw + ru, key);
+            atomic_min_u64(bw + rv, key);
+        } else {
+            unsigned* be = p.best_e + map * n;
+            if (bw[ru] == key) atomic_min_u32(be + ru, (unsigned)e);
+            if (bw[rv] == key) atomic_min_u32(be + rv, (unsigned)e);
+        }
+    }
+};
+struct MstUnite : ElemBase {
+    using Params = MstRoundParams;
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
+        const long long i = (long long)bx * THREADS + tid;
+        if (i >= p.total) return;
+        const int n = p.H * p.W;
+        const long long map = i / n;
+        const unsigned e = p.best_e[i];        // only entries of (start-of-round) roots can be set
+        if (e == ~0u) return;
+        int u, v;
+        edge_ends((int)e, n, p.H, p.W, u, v);
+        const float* w = p.w + map * n;
+        // value[u] + 2pi inc[u] continuous with value[v] + 2pi inc[v]:  inc[v] = inc[u] - jump(u, v)
+        const int delta = -jump_between((double)w[u], (double)w[v]);
+        if (pot_unite(p.PO + map * n, u, v, delta)) atomic_add_i32(p.merges, 1);
+    }
+};
+struct MstFlatten : ElemBase {
+    using Params = MstRoundParams;
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
+        const long long i = (long long)bx * THREADS + tid;
+        if (i >= p.total) return;
+        const int n = p.H * p.W;
+        po_t* PO = p.PO + (i / n) * n;
+        const int px = (int)(i % n);
+        int root, pot;
+        pot_find(PO, px, root, pot);
+        if (root != px) PO[px] = po_pack(root, pot);     // one 64-bit store: concurrent walks stay consistent
+    }
+};
+struct MstApply : ElemBase {
+    using Params = MstRoundParams;
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
+        const long long i = (long long)bx * THREADS + tid;
+        if (i >= p.total) return;
+        const int n = p.H * p.W;
+        const po_t* PO = p.PO + (i / n) * n;
+        int root, pot;
+        pot_find(PO, (int)(i % n), root, pot);
+        p.out[i] = (float)((double)p.w[i] + 2.0 * kPiD * (double)pot);
+    }
+};
+
+// ---- forward row transform of z = phi0 + i*phi1 read from a materialised phases array ---------------
+struct RowPhaseFwdParams {
+    const float* phases;   // [F][2][H][W]
+    cf* w3;                // column-blocked, see w3_index
+    const cf* tw;
+    int H;
+};
+template <int L, int G>
+struct RowPhaseFwd : AllPhases {
+    using FF = Fft<L, -1, float>;
+    using GL = GroupLayout<L, G>;
+    using Params = RowPhaseFwdParams;
+    static constexpr bool BLOCKED_TILES = false;
+    static constexpr bool PIPELINED = false;
+    static constexpr int SYNC_THREADS = 0;
+    static constexpr int MIN_BLOCKS = 1;
+    static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 4;
+    using TW = SmemTwiddles<FF, THREADS>;
+    static constexpr int SMEM_BYTES = TW::TW_BYTES + G * GL::STRIDE * (int)sizeof(cf);
+    FCD_HD static void prologue(const Params& p, int tid, unsigned char* smem) { TW::load(p.tw, tid, smem); }
+    struct State { cf v[16]; };
+
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem_all, State& st) {
+        const cf* tw = reinterpret_cast<const cf*>(smem_all);
+        const int g = tid / TPF, t = tid % TPF;
+        cf* s = reinterpret_cast<cf*>(smem_all + TW::TW_BYTES) + g * GL::STRIDE;
+        const int W = L;
+        const int y = bx * G + g, f = by;
+        if constexpr (PH == 0) {
+            const float* p0 = p.phases + (((long long)f * 2 + 0) * p.H + y) * W;
+            const float* p1 = p.phases + (((long long)f * 2 + 1) * p.H + y) * W;
+            FCD_UNROLL
+            for (int m = 0; m < 16; ++m) st.v[m] = mk<float>(p0[t + TPF * m], p1[t + TPF * m]);
+            FF::stepA(st.v, t, s);
+        } else if constexpr (PH == 1) {
+            FF::stepB(st.v, t, s, tw);
+        } else if constexpr (PH == 2) {
+            FF::stepC(st.v, t, s);
+        } else {
+            FF::stepD(st.v, t, s, tw);
+            FCD_UNROLL
+            for (int m = 0; m < 16; ++m) p.w3[w3_index(f, t + TPF * m, y, p.H, W)] = st.v[m];
+        }
+    }
+};
+
+}  // namespace fcd

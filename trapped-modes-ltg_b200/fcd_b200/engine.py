@@ -106,6 +106,22 @@ def to_device_image(a, device, allow_f64=True) -> torch.Tensor:
     return t.to(device, non_blocking=True).contiguous()
 
 
+UNWRAP_MODES = {"off": 0, "scan": 1, "herraez": 2, "guided": 2, "auto": 3}
+
+
+def unwrap_mode(unwrap) -> int:
+    """False / 'off' -> 0;  True / 'scan' -> 1 (row/column scan: the fast path, exact where the
+    wrapped phases have no residues);  'herraez' -> 2 (reliability-guided, what
+    skimage.restoration.unwrap_phase does, pyfcd/fcd.py:119);  'auto' -> 3 (scan, then the frames
+    whose phases have residues are redone with 'herraez')."""
+    if isinstance(unwrap, str):
+        try:
+            return UNWRAP_MODES[unwrap]
+        except KeyError:
+            raise ValueError(f"unwrap must be a bool or one of {sorted(UNWRAP_MODES)}") from None
+    return 1 if unwrap else 0
+
+
 class HeightMapPlan:
     """One plan = one frame shape on one GPU.  Owns the workspaces, the twiddle tables and,
     after ``bind``, the per-reference state (carrier disks, ccsgn, integration coefficients).
@@ -221,9 +237,11 @@ class HeightMapPlan:
 
     # ---- per-frame path ------------------------------------------------------------------
     def execute(self, frames: torch.Tensor, out: Optional[torch.Tensor] = None, phases=False,
-                mask: Optional[torch.Tensor] = None, unwrap: bool = True):
+                mask: Optional[torch.Tensor] = None, unwrap=True):
         """frames: CUDA float32 [n, H, W] (or [H, W]).  Returns height maps float32 [n, H, W]
-        and, when ``phases`` is True or a tensor, phases float32 [n, 2, H, W]."""
+        and, when ``phases`` is True or a tensor, phases float32 [n, 2, H, W].
+        ``unwrap``: see :func:`unwrap_mode`."""
+        mode = unwrap_mode(unwrap)
         kinds = {torch.float32: 0, torch.uint8: 1, torch.uint16: 2}
         if not (isinstance(frames, torch.Tensor) and frames.is_cuda and frames.dtype in kinds):
             raise TypeError("frames must be a CUDA float32 / uint8 / uint16 tensor "
@@ -255,12 +273,58 @@ class HeightMapPlan:
                 mask_stride = self.shape[0] * self.shape[1]
             self._check_image(mk)
         with torch.cuda.device(self.device):
-            check(self.lib, self.lib.fcd_execute_typed(self._h, _ptr(fr), kind, int(n), _ptr(out), _ptr(ph), _ptr(mk),
-                                                       int(mask_stride), int(bool(unwrap)), _stream_ptr()))
+            if mode == 3:
+                self._execute_auto(fr, kind, out, ph, mk, mask_stride)
+            else:
+                check(self.lib, self.lib.fcd_execute_typed(self._h, _ptr(fr), kind, int(n), _ptr(out), _ptr(ph),
+                                                           _ptr(mk), int(mask_stride), mode, _stream_ptr()))
         if squeeze:
             out = out.view(self.shape) if out.dim() == 3 else out
             ph = ph[0] if ph is not None else None
         return (out, ph) if ph is not None else out
+
+    def _execute_auto(self, fr, kind, out, ph, mk, mask_stride) -> None:
+        """Scan unwrap per chunk with the phases materialised, residue count per map, and the
+        reliability-guided unwrap for the frames that have residues (where the scan result
+        depends on the path and the reference's unwrapper has to be followed)."""
+        n, px = int(fr.shape[0]), self.shape[0] * self.shape[1]
+        out3 = out.view((n,) + self.shape)
+        step = self.frames_per_launch
+        scratch = None if ph is not None else torch.empty((min(step, n), 2) + self.shape, dtype=torch.float32,
+                                                           device=self.device)
+        self.last_guided_frames = []
+        for c0 in range(0, n, step):
+            c1 = min(n, c0 + step)
+            ph_c = ph[c0:c1] if ph is not None else scratch[:c1 - c0]
+            mk_c = None if mk is None else (mk[c0:c1] if mask_stride else mk)
+            check(self.lib, self.lib.fcd_execute_typed(self._h, _ptr(fr[c0:c1]), kind, c1 - c0, _ptr(out3[c0:c1]),
+                                                       _ptr(ph_c), _ptr(mk_c), int(mask_stride), 1, _stream_ptr()))
+            counts = (ctypes.c_int * (2 * (c1 - c0)))()
+            check(self.lib, self.lib.fcd_count_residues(self._h, _ptr(ph_c), 2 * (c1 - c0), counts, _stream_ptr()))
+            bad = [i for i in range(c1 - c0) if counts[2 * i] or counts[2 * i + 1]]
+            if not bad:
+                continue
+            self.last_guided_frames += [c0 + i for i in bad]
+            idx = torch.tensor(bad, device=self.device)
+            fr_b = fr[c0:c1].index_select(0, idx).contiguous()
+            out_b = torch.empty((len(bad),) + self.shape, dtype=torch.float32, device=self.device)
+            ph_b = torch.empty((len(bad), 2) + self.shape, dtype=torch.float32, device=self.device)
+            mk_b = None if mk is None else (mk[c0:c1].index_select(0, idx).contiguous() if mask_stride else mk)
+            check(self.lib, self.lib.fcd_execute_typed(self._h, _ptr(fr_b), kind, len(bad), _ptr(out_b), _ptr(ph_b),
+                                                       _ptr(mk_b), int(mask_stride), 2, _stream_ptr()))
+            out3[c0:c1].index_copy_(0, idx, out_b)
+            ph_c.index_copy_(0, idx, ph_b)
+
+    def unwrap_phase(self, wrapped: torch.Tensor) -> torch.Tensor:
+        """Reliability-guided unwrap of [..., H, W] float32 maps (skimage.restoration.unwrap_phase as
+        called at pyfcd/fcd.py:119); pixel (0, 0) of every map keeps its value."""
+        w = wrapped.to(self.device).to(torch.float32).contiguous()
+        self._check_image(w)
+        n = w.numel() // (self.shape[0] * self.shape[1])
+        out = torch.empty_like(w)
+        with torch.cuda.device(self.device):
+            check(self.lib, self.lib.fcd_unwrap_phase(self._h, _ptr(w), int(n), _ptr(out), _stream_ptr()))
+        return out
 
     def set_height(self, layers=None, height=None) -> None:
         """Change the effective height of the bound reference (fcd.py:16-25) without re-binding."""
@@ -354,7 +418,7 @@ def get_plan(shape, frames_per_launch: int = 16, device=None) -> HeightMapPlan:
     return plan
 
 
-def compute_height_maps(reference, frames, square_size, layers=None, height=None, unwrap=True,
+def compute_height_maps(reference, frames, square_size, layers=None, height=None, unwrap="auto",
                         return_phases=False, mask=None, plan: Optional[HeightMapPlan] = None,
                         frames_per_launch: int = 16, out=None):
     """Batched equivalent of calling fcd.compute_height_map(reference, frame, ...) for every

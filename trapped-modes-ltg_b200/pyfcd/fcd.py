@@ -16,7 +16,10 @@ class fcd:
         """Reference: pyfcd/fcd.py:14-35.  Returns (height_map float64 [N0,N1],
         phases float64 [2,N0,N1], calibration_factor), caller-owned writable numpy arrays.
         The arithmetic is the fused float32 CUDA pipeline (carrier detection and ccsgn in
-        float64); `phases` equal the reference's up to one global 2*pi*k per map."""
+        float64); `phases` equal the reference's up to one global 2*pi*k per map.
+        unwrap=True follows the reference's unwrapper: the scan path where the wrapped phases
+        have no residues (every path gives the same answer there), the reliability-guided
+        device unwrap (csrc/fcd_unwrap.cuh) where they do."""
         height = _eng.resolve_height(layers, height)
         plan = _eng.get_plan(np.shape(reference), 1)
         # The reference recomputes the carriers on every call (fcd.py:27).  Callers loop over
@@ -34,7 +37,7 @@ class fcd:
             calibration_factor = plan.bind(ref_dev, square_size=square_size, height=height)
             plan._dropin_key = (ref_dev, float(square_size))
         frame = _eng.to_device_image(displaced, plan.device, allow_f64=False)
-        height_map, phases = plan.execute(frame, phases=True, unwrap=unwrap)
+        height_map, phases = plan.execute(frame, phases=True, unwrap="auto" if unwrap is True else unwrap)
         return (height_map.to(torch.float64).cpu().numpy(), phases.to(torch.float64).cpu().numpy(),
                 calibration_factor)
 
@@ -91,7 +94,16 @@ class fcd:
             mask = torch.from_numpy(np.ascontiguousarray(carrier.mask)).to(dev)
             cc = torch.from_numpy(np.ascontiguousarray(carrier.ccsgn)).to(dev).to(torch.complex128)
             ang = -torch.angle(plan.fft2_c128(f * mask, inverse=True) * cc)
-            phases[i] = (_unwrap_scan(ang) if unwrap else ang).cpu().numpy()
+            if unwrap:
+                w32 = ang.to(torch.float32)
+                if plan.count_residues(w32)[0]:
+                    # path-dependent: follow the reference's unwrapper (integer field from the
+                    # float32 device unwrap, applied to the float64 angles)
+                    k = torch.round((plan.unwrap_phase(w32) - w32) / (2.0 * np.pi)).to(torch.float64)
+                    ang = ang + 2.0 * np.pi * k
+                else:
+                    ang = _unwrap_scan(ang)
+            phases[i] = ang.cpu().numpy()
         return phases
 
     @classmethod
