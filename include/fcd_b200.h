@@ -102,6 +102,36 @@ int fcd_count_residues(fcd_plan* plan, const float* phases_dev, int n_maps, int*
  * differs by one global 2*pi*k).  This is what fcd_execute runs when unwrap == 2. */
 int fcd_unwrap_phase(fcd_plan* plan, const float* wrapped_dev, int n_maps, float* unwrapped_dev, void* stream);
 
+/* Temporal harmonic analysis of a device-resident stack of height maps maps_dev[n][rows][cols]
+ * float32, for all spatial blocks at once: a grid of block_rows x block_cols blocks of
+ * block_size^2 pixels from the top-left corner (the reference: block_size = rows // blocks_per_row,
+ * block_rows = block_cols = blocks_per_row, analyze.py:572-573; a row band of a frame-sharded stack
+ * holds fewer block rows).  Replaces analyze.block_amplitude / analyze.block_split
+ * (pydata/analyze.py:542-641, 365-417), which re-read every map file once per block.
+ *
+ * fcd_temporal_mean_spectrum: np.nanmean(|np.fft.fft(block stack, axis=-1)|, axis=(0,1)) at the
+ *   non-negative frequencies (analyze.py:603-614), pixels that are zero in first_map_dev excluded
+ *   (analyze.py:568,590) and `zero` subtracted (analyze.py:585).  mean_out: host,
+ *   [blocks][npos] float64 with npos = n/2 (n even) or (n+1)/2; valid_out: host, [blocks] valid-pixel
+ *   counts (0 -> NaN row).  n must satisfy fcd_temporal_frames_supported (a power of two in
+ *   [64, 4096], or at most 2048 through a chirp convolution).
+ * fcd_temporal_accumulate: adds frames [t0, t0 + n_chunk) of an n_total-frame series to the
+ *   DFT sums of n_bins bins per block (bins: host, [blocks][n_bins]); acc_dev is
+ *   [n_bins][2][rows*cols] float64 (init != 0 overwrites).  Any n_total; additive over chunks
+ *   and over frame shards (sum the acc arrays of all ranks).
+ * fcd_temporal_finalize: amplitude (|X|/n for the first bin, 2|X|/n after) and phase planes in
+ *   the reference's (rows, cols, n_bins + 1) float64 layout (analyze.py:629-638), NaN where
+ *   first_map_dev is zero. */
+int fcd_temporal_mean_spectrum(fcd_plan* plan, const float* maps_dev, int n_frames, int rows, int cols,
+                               const float* first_map_dev, float zero, int block_size, int block_rows, int block_cols,
+                               double* mean_out, int* valid_out, void* stream);
+int fcd_temporal_frames_supported(int n_frames);
+int fcd_temporal_accumulate(fcd_plan* plan, const float* maps_dev, int n_chunk, int t0, int n_total, int rows, int cols,
+                            float zero, int block_size, int block_rows, int block_cols, const int* bins, int n_bins,
+                            double* acc_dev, int init, void* stream);
+int fcd_temporal_finalize(fcd_plan* plan, const double* acc_dev, int n_bins, int n_total, int rows, int cols,
+                          const float* first_map_dev, double* amps_dev, double* phases_dev, void* stream);
+
 /* Floating-structure mask of each frame: box filter of width `smoothed`, threshold at the mean of
  * the filtered image, largest 8-connected region below it.  Bit-exact replacement of
  * analyze.mask (pydata/analyze.py:43-100).  frames_dev [n][rows][cols] float32 ->

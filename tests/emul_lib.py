@@ -112,6 +112,41 @@ class EmulPlan:
         _native.check(self.lib, self.lib.fcd_unwrap_phase(self.h, _p(w), n, _p(out), None))
         return out
 
+    def temporal_mean_spectrum(self, maps, first, zero, bpr):
+        maps = np.ascontiguousarray(maps, dtype=np.float32)
+        n, rows, cols = maps.shape
+        first = None if first is None else np.ascontiguousarray(first, dtype=np.float32)
+        npos = n // 2 if n % 2 == 0 else (n + 1) // 2
+        mean = np.zeros((bpr * bpr, npos), np.float64)
+        valid = np.zeros(bpr * bpr, np.int32)
+        _native.check(self.lib, self.lib.fcd_temporal_mean_spectrum(
+            self.h, _p(maps), n, rows, cols, _p(first), float(zero), rows // bpr, bpr, bpr,
+            mean.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), valid.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), None))
+        return mean, valid
+
+    def temporal_harmonics(self, maps, bins, n_total=None, t0=0, zero=0.0, bpr=2, first=None, chunks=(None,)):
+        maps = np.ascontiguousarray(maps, dtype=np.float32)
+        n, rows, cols = maps.shape
+        n_total = n if n_total is None else n_total
+        bins = np.ascontiguousarray(bins, dtype=np.int32)
+        nb = bins.shape[1]
+        acc = np.zeros((nb, 2, rows * cols), np.float64)
+        edges = [0] + [c for c in chunks if c is not None] + [n]
+        for a, b in zip(edges[:-1], edges[1:]):
+            _native.check(self.lib, self.lib.fcd_temporal_accumulate(
+                self.h, _p(maps[a:b]), b - a, t0 + a, n_total, rows, cols, float(zero), rows // bpr, bpr, bpr,
+                bins.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), nb, _p(acc), int(a == 0), None))
+        return acc
+
+    def temporal_finalize(self, acc, n_total, shape, first=None):
+        nb = acc.shape[0]
+        first = None if first is None else np.ascontiguousarray(first, dtype=np.float32)
+        amps = np.zeros(tuple(shape) + (nb + 1,), np.float64)
+        phases = np.zeros_like(amps)
+        _native.check(self.lib, self.lib.fcd_temporal_finalize(self.h, _p(acc), nb, n_total, shape[0], shape[1], _p(first),
+                                                               _p(amps), _p(phases), None))
+        return amps, phases
+
     def set_height(self, height):
         _native.check(self.lib, self.lib.fcd_set_height(self.h, float(height)))
 

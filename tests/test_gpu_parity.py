@@ -266,7 +266,7 @@ def test_integer_frames_residues_and_reference_cache(api, golden):
     n0 = api["eng"].get_plan((256, 256), 1).launch_count
     b, _, _ = fcd.compute_height_map(g("ref").copy(), g("frame"), sq, height=0.5)
     n1 = api["eng"].get_plan((256, 256), 1).launch_count
-    assert n1 - n0 <= 7                      # only the per-frame kernels ran
+    assert n1 - n0 <= 8                      # only the per-frame kernels ran (7 stages + the residue count)
     assert np.allclose(b, a / 0.5, rtol=1e-6, atol=1e-9)
     c, _, _ = fcd.compute_height_map(g("ref") * 0.5, g("frame") * 0.5, sq, height=1.0)   # different reference -> re-bind
     assert rel_l2(c, a) < 1e-5

@@ -105,6 +105,14 @@ FCD_HD void async_copy8(void* smem_dst, const void* gsrc) {
     *reinterpret_cast<cf*>(smem_dst) = *reinterpret_cast<const cf*>(gsrc);
 #endif
 }
+FCD_HD void async_copy4(void* smem_dst, const void* gsrc) {
+#if defined(__CUDA_ARCH__)
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+#else
+    *reinterpret_cast<float*>(smem_dst) = *reinterpret_cast<const float*>(gsrc);
+#endif
+}
 FCD_HD void async_wait_all() {
 #if defined(__CUDA_ARCH__)
     asm volatile("cp.async.wait_all;" ::: "memory");

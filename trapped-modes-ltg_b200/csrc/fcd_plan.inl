@@ -6,12 +6,14 @@
 #include <algorithm>
 #include <array>
 #include <cmath>
+#include <complex>
 #include <unordered_map>
 
 #include "fcd_b200.h"
 #include "fcd_generic.cuh"
 #include "fcd_mask.cuh"
 #include "fcd_unwrap.cuh"
+#include "fcd_temporal.cuh"
 #include "fcd_launch.cuh"
 
 namespace fcd {
@@ -514,6 +516,139 @@ struct PlanImpl {
         }
     }
 
+    // ------------------------------------------------------------------ temporal analysis ----
+    // analyze.block_amplitude (pydata/analyze.py:542-641): see fcd_temporal.cuh
+    template <int L> struct TuneT { static constexpr int G = L >= 4096 ? 2 : (L >= 2048 ? 4 : 8); };
+    int t_len = 0, t_n = 0;                 // cached tables: transform length, number of frames
+    rt::DevBuf<cf> t_tw, t_chirp, t_bspec;
+    rt::DevBuf<double> t_mean, t_twd;
+    rt::DevBuf<int> t_valid;
+
+    static int temporal_length(int n_frames) {        // 0: not supported
+        if (n_frames >= 64 && n_frames <= 4096 && (n_frames & (n_frames - 1)) == 0) return n_frames;
+        int l = 64;
+        while (l < 2 * n_frames - 1) l *= 2;
+        return l <= 4096 ? l : 0;
+    }
+    static void host_fft(std::vector<std::complex<double>>& a) {   // in place, forward, power of two
+        const size_t n = a.size();
+        for (size_t i = 1, j = 0; i < n; ++i) {
+            size_t bit = n >> 1;
+            for (; j & bit; bit >>= 1) j ^= bit;
+            j ^= bit;
+            if (i < j) std::swap(a[i], a[j]);
+        }
+        for (size_t len = 2; len <= n; len <<= 1) {
+            for (size_t k = 0; k < len / 2; ++k) {
+                const double ang = -2.0 * M_PI * (double)k / (double)len;
+                const std::complex<double> w(std::cos(ang), std::sin(ang));
+                for (size_t i = k; i < n; i += len) {
+                    const std::complex<double> u = a[i], v = a[i + len / 2] * w;
+                    a[i] = u + v;
+                    a[i + len / 2] = u - v;
+                }
+            }
+        }
+    }
+    void temporal_tables(int n_frames, rt::stream_t s) {
+        const int len = temporal_length(n_frames);
+        if (!len) rt::fail("temporal spectrum: the number of frames must be a power of two in [64, 4096] or at most 2048");
+        if (len == t_len && n_frames == t_n) return;
+        FCD_DISPATCH_L(len, { t_tw.upload(Fft<L, -1, float>::make_table(), s); })
+        if (len != n_frames) {
+            // Bluestein: X[k] = conj(c[k]) * sum_t (x[t] conj(c[t])) c[k - t],  c[m] = exp(i pi m^2 / N)
+            std::vector<std::complex<double>> c((size_t)n_frames), b((size_t)len, 0.0);
+            for (int m = 0; m < n_frames; ++m) {
+                const long long q = ((long long)m * m) % (2LL * n_frames);
+                const double ang = M_PI * (double)q / (double)n_frames;
+                c[m] = {std::cos(ang), std::sin(ang)};
+                b[m] = c[m];
+                if (m) b[len - m] = c[m];
+            }
+            host_fft(b);
+            std::vector<cf> hc((size_t)n_frames), hb((size_t)len);
+            for (int m = 0; m < n_frames; ++m) hc[m] = mk<float>((float)c[m].real(), (float)c[m].imag());
+            for (int m = 0; m < len; ++m) hb[m] = mk<float>((float)(b[m].real() / len), (float)(b[m].imag() / len));
+            t_chirp.upload(hc, s);
+            t_bspec.upload(hb, s);
+        }
+        t_len = len; t_n = n_frames;
+    }
+    static int temporal_npos(int n_frames) { return n_frames % 2 == 0 ? n_frames / 2 : (n_frames + 1) / 2; }   // fftfreq >= 0
+
+    static void temporal_geometry(int rows, int cols, int bs, int brows, int bcols) {
+        if (rows < 1 || cols < 1 || bs < 1 || brows < 1 || bcols < 1) rt::fail("temporal analysis: bad geometry");
+        if ((long long)bs * brows > rows || (long long)bs * bcols > cols) rt::fail("temporal analysis: blocks do not fit the maps");
+    }
+
+    void temporal_mean_spectrum(const float* maps, int n_frames, int rows, int cols, const float* first, float zero,
+                                int bs, int brows, int bcols, double* mean_host, int* valid_host, rt::stream_t s) {
+        temporal_geometry(rows, cols, bs, brows, bcols);
+        if (n_frames < 2) rt::fail("temporal spectrum needs at least two frames");
+        temporal_tables(n_frames, s);
+        const int nblk = brows * bcols, npos = temporal_npos(n_frames);
+        t_mean.alloc((size_t)nblk * npos);
+        t_valid.alloc((size_t)nblk);
+        rt::dmemset(t_mean.ptr, 0, sizeof(double) * (size_t)nblk * npos, s);
+        rt::dmemset(t_valid.ptr, 0, sizeof(int) * (size_t)nblk, s);
+        const long long total = (long long)rows * cols;
+        const long long segs = (long long)bs * brows * bcols;
+        launch<BlockValidCount>(blocks_for(segs), 1, s, BlockValidParams{first, t_valid.ptr, rows, cols, bs, brows, bcols, segs});
+        TemporalSpecParams p{maps, first, t_tw.ptr, t_chirp.ptr, t_bspec.ptr, t_mean.ptr, zero, n_frames, npos, rows, cols, bs, brows, bcols};
+        const bool blue = t_len != n_frames;
+        FCD_DISPATCH_L(t_len, {
+            constexpr int G = TuneT<L>::G;
+            if (bs % G != 0) rt::fail("temporal spectrum: the block size must be a multiple of 8");
+            if (blue) launch<TemporalSpectrum<L, G, true>>(bs * (bs / G), nblk, s, p);
+            else launch<TemporalSpectrum<L, G, false>>(bs * (bs / G), nblk, s, p);
+        })
+        rt::d2h(mean_host, t_mean.ptr, sizeof(double) * (size_t)nblk * npos, s);
+        rt::d2h(valid_host, t_valid.ptr, sizeof(int) * (size_t)nblk, s);
+        for (int b = 0; b < nblk; ++b)                                   // np.nanmean over the block's valid pixels
+            for (int k = 0; k < npos; ++k)
+                mean_host[(size_t)b * npos + k] = valid_host[b] ? mean_host[(size_t)b * npos + k] / valid_host[b] : nan_f64();
+    }
+
+    void temporal_accumulate(const float* maps, int n_chunk, int t0, int n_total, int rows, int cols, float zero,
+                             int bs, int brows, int bcols, const int* bins, int n_bins, double* acc, int init,
+                             rt::stream_t s) {
+        temporal_geometry(rows, cols, bs, brows, bcols);
+        if (n_bins < 1 || n_bins > kMaxHarmonicBins) rt::fail("temporal harmonics: 1..8 bins per block");
+        if (n_chunk < 0 || t0 < 0 || n_total < 1 || t0 + n_chunk > n_total) rt::fail("temporal harmonics: bad frame range");
+        const int nblk = brows * bcols;
+        std::vector<double> tw((size_t)std::max(n_chunk, 1) * nblk * n_bins * 2);
+        for (int f = 0; f < n_chunk; ++f)
+            for (int b = 0; b < nblk; ++b)
+                for (int j = 0; j < n_bins; ++j) {
+                    const long long q = ((long long)bins[b * n_bins + j] * (t0 + f)) % n_total;    // exact phase reduction
+                    const double ang = 2.0 * M_PI * (double)q / (double)n_total;
+                    double* w = &tw[(((size_t)f * nblk + b) * n_bins + j) * 2];
+                    w[0] = std::cos(ang);
+                    w[1] = -std::sin(ang);
+                }
+        t_twd.upload(tw, s);
+        const long long total = (long long)rows * cols;
+        const HarmonicAccParams hp{maps, t_twd.ptr, acc, zero, n_chunk, n_bins, rows, cols, bs, brows, bcols, init, total};
+        switch (n_bins) {
+            case 1: launch<HarmonicAccumulate<1>>(blocks_for(total), 1, s, hp); break;
+            case 2: launch<HarmonicAccumulate<2>>(blocks_for(total), 1, s, hp); break;
+            case 3: launch<HarmonicAccumulate<3>>(blocks_for(total), 1, s, hp); break;
+            case 4: launch<HarmonicAccumulate<4>>(blocks_for(total), 1, s, hp); break;
+            case 5: launch<HarmonicAccumulate<5>>(blocks_for(total), 1, s, hp); break;
+            case 6: launch<HarmonicAccumulate<6>>(blocks_for(total), 1, s, hp); break;
+            case 7: launch<HarmonicAccumulate<7>>(blocks_for(total), 1, s, hp); break;
+            default: launch<HarmonicAccumulate<8>>(blocks_for(total), 1, s, hp); break;
+        }
+        rt::sync(s);    // t_twd is reused by the next call
+    }
+
+    void temporal_finalize(const double* acc, int n_bins, int n_total, int rows, int cols, const float* first,
+                           double* amps, double* phases, rt::stream_t s) {
+        if (n_bins < 1 || n_bins > kMaxHarmonicBins || n_total < 1) rt::fail("temporal harmonics: bad arguments");
+        const long long total = (long long)rows * cols;
+        launch<HarmonicFinalize>(blocks_for(total), 1, s, HarmonicFinParams{acc, first, amps, phases, n_bins, n_total, total});
+    }
+
     // ------------------------------------------------------------------ structure mask / centre ----
     // analyze.mask (pydata/analyze.py:43-100) and analyze.center (pydata/analyze.py:104-140)
     static constexpr int kMaskChunk = 16;
@@ -788,6 +923,36 @@ int fcd_unwrap_phase(fcd_plan* plan, const float* wrapped_dev, int n_maps, float
     return fcd_guard([&] {
         plan->impl.unwrap_maps(wrapped_dev, n_maps, unwrapped_dev, stream);
         fcd::rt::sync(stream);
+    });
+}
+
+int fcd_temporal_mean_spectrum(fcd_plan* plan, const float* maps_dev, int n_frames, int rows, int cols,
+                               const float* first_map_dev, float zero, int block_size, int block_rows, int block_cols,
+                               double* mean_out, int* valid_out, void* stream) {
+    if (!plan || !maps_dev || !mean_out || !valid_out) { g_fcd_error = "null argument"; return FCD_ERR_INVALID; }
+    return fcd_guard([&] {
+        plan->impl.temporal_mean_spectrum(maps_dev, n_frames, rows, cols, first_map_dev, zero, block_size, block_rows,
+                                          block_cols, mean_out, valid_out, stream);
+    });
+}
+
+int fcd_temporal_frames_supported(int n_frames) { return fcd::PlanImpl::temporal_length(n_frames) != 0; }
+
+int fcd_temporal_accumulate(fcd_plan* plan, const float* maps_dev, int n_chunk, int t0, int n_total, int rows, int cols,
+                            float zero, int block_size, int block_rows, int block_cols, const int* bins, int n_bins,
+                            double* acc_dev, int init, void* stream) {
+    if (!plan || (n_chunk > 0 && !maps_dev) || !bins || !acc_dev) { g_fcd_error = "null argument"; return FCD_ERR_INVALID; }
+    return fcd_guard([&] {
+        plan->impl.temporal_accumulate(maps_dev, n_chunk, t0, n_total, rows, cols, zero, block_size, block_rows, block_cols,
+                                       bins, n_bins, acc_dev, init, stream);
+    });
+}
+
+int fcd_temporal_finalize(fcd_plan* plan, const double* acc_dev, int n_bins, int n_total, int rows, int cols,
+                          const float* first_map_dev, double* amps_dev, double* phases_dev, void* stream) {
+    if (!plan || !acc_dev || !amps_dev || !phases_dev) { g_fcd_error = "null argument"; return FCD_ERR_INVALID; }
+    return fcd_guard([&] {
+        plan->impl.temporal_finalize(acc_dev, n_bins, n_total, rows, cols, first_map_dev, amps_dev, phases_dev, stream);
     });
 }
 

@@ -35,6 +35,17 @@ PROTOTYPES = {
     "fcd_set_height": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double]),
     "fcd_count_residues": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, c_int_p, ctypes.c_void_p]),
     "fcd_unwrap_phase": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "fcd_temporal_mean_spectrum": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                  ctypes.c_void_p, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                  c_double_p, c_int_p, ctypes.c_void_p]),
+    "fcd_temporal_frames_supported": (ctypes.c_int, [ctypes.c_int]),
+    "fcd_temporal_accumulate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                               ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int,
+                                               ctypes.c_int, c_int_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                               ctypes.c_void_p]),
+    "fcd_temporal_finalize": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_void_p]),
     "fcd_structure_mask": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                           ctypes.c_void_p]),
     "fcd_mask_center": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, c_int_p, ctypes.c_void_p]),

@@ -10,7 +10,7 @@ REPO = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB = os.path.join(PKG_DIR, "libfcd_b200.so")
 SOURCES = ["fcd_b200.cu"]
-HEADERS = ["fft_core.cuh", "fcd_kernels.cuh", "fcd_generic.cuh", "fcd_mask.cuh", "fcd_unwrap.cuh", "fcd_launch.cuh", "fcd_plan.inl"]
+HEADERS = ["fft_core.cuh", "fcd_kernels.cuh", "fcd_generic.cuh", "fcd_mask.cuh", "fcd_unwrap.cuh", "fcd_temporal.cuh", "fcd_launch.cuh", "fcd_plan.inl"]
 
 
 def _nvcc() -> str:
