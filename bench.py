@@ -43,7 +43,8 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=2048)
     ap.add_argument("--frames", type=int, default=1000, help="frames per GPU per step (device-resident leg)")
-    ap.add_argument("--frames-per-launch", type=int, default=32)
+    ap.add_argument("--frames-per-launch", type=int, default=0,
+                    help="frames per kernel wave; 0 = 128 up to 2048^2, 32 above (workspace is ~66 MB per 2048^2 frame)")
     ap.add_argument("--e2e-frames", type=int, default=256, help="frames per step of the host-buffer leg")
     ap.add_argument("--e2e-chunk", type=int, default=8, help="frames per host<->device copy of the host-buffer leg")
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -241,6 +242,8 @@ def run_ours(args):
 
     n, F = args.size, args.frames
     P = n * n
+    if args.frames_per_launch <= 0:
+        args.frames_per_launch = 128 if n <= 2048 else 32
     plan = HeightMapPlan((n, n), args.frames_per_launch, dev)
     ref, frames = make_frames_gpu(n, F, SEED + rank, dev, peak_range=tuple(args.peak_px))
     from oracle import fcd_oracle as o

@@ -28,11 +28,15 @@ constexpr float kInvTwoPiF = 0.15915494309189533577f;
 
 FCD_HD int imin(int a, int b) { return a < b ? a : b; }
 
-FCD_HD float fast_div(float a, float b) {
+// 1/x as one MUFU.RCP.  Without .ftz the compiler wraps every reciprocal in a denormal rescue
+// (FMUL by 2^24, FSETP, FSEL, predicated FMUL: SASS of profiles r01_m3); callers keep x >= 1e-30.
+FCD_HD float fast_rcp(float x) {
 #if defined(__CUDA_ARCH__)
-    return __fdividef(a, b);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 #else
-    return a / b;
+    return 1.0f / x;
 #endif
 }
 
@@ -42,8 +46,8 @@ FCD_HD float fast_div(float a, float b) {
 // np.angle(0) = 0 is preserved.
 FCD_HD float fast_atan2f(float y, float x) {
     const float ax = fabsf(x), ay = fabsf(y);
-    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-    const float a = fast_div(mn, mx);
+    const float mx = fmaxf(fmaxf(ax, ay), 1e-30f), mn = fminf(ax, ay);   // (0, 0) -> a = 0 -> angle 0
+    const float a = mn * fast_rcp(mx);
     const float s = a * a;
     float r = -0.004054565913975239f;
     r = r * s + 0.021862953901290894f;
@@ -56,7 +60,6 @@ FCD_HD float fast_atan2f(float y, float x) {
     r = r * a;
     r = (ay > ax) ? 1.57079632679489661923f - r : r;
     r = (x < 0.f) ? 3.14159265358979323846f - r : r;
-    r = (mx > 0.f) ? r : 0.f;
     return copysignf(r, y);
 }
 
@@ -832,7 +835,7 @@ struct ColIntegrate : AllPhases {
                     const float kyb = (kr == H / 2 - 1) ? 0.f : kym;                     // quirk-zeroed ky[-kr]
                     float k2 = kxv * kxv + kyv * kyv;
                     if (kr == 0 && kc == 0) k2 = 1.f;
-                    const float ik2 = fast_div(1.0f, k2);
+                    const float ik2 = fast_rcp(k2);
                     // a(k), a(-k) and b(k), b(-k): coefficients of Phi0, Phi1 in hhat / i
                     const float a_p = kxa * p.f1r - kya * p.f1c, a_m = kxb * p.f1r - kyb * p.f1c;
                     const float b_p = kya * p.f0c - kxa * p.f0r, b_m = kyb * p.f0c - kxb * p.f0r;
