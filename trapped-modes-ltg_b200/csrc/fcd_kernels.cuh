@@ -482,7 +482,7 @@ struct RowDemod {
                     for (int ii = 0; ii < 2; ++ii) {
                         const int c = (t + TPF * ii - p0) & (M1 - 1);
                         const int pp = (p0 + c) & (W - 1);
-                        FI::stepA_single(nx[i * 2 + ii], pp / M1, ii, t, sb);
+                        FI::stepA_single(nx[i * 2 + ii], pp / M1, ii, t, sb, tw);
                     }
                 }
             } else {

@@ -170,7 +170,8 @@ struct Fft {
     // W_{PP*R}^{k*a}, k in [0,PP), a in [1,R)  ->  table[off + a*PP + k].
     // Block of the middle pass (three-pass plans) first, then the block of the last pass.
     static constexpr int TW_MID = THREE ? R1 * R2 : 0;
-    static constexpr int TW_ELEMS = TW_MID + L;
+    static constexpr int TW_W8 = TW_MID + L;          // W_8^m, m = 0..7 (pruned first pass)
+    static constexpr int TW_ELEMS = TW_W8 + 8;
 
     // host: build the table (forward sign; DIR=+1 conjugates on load)
     static std::vector<cx<T>> make_table() {
@@ -184,6 +185,15 @@ struct Fft {
         };
         if (THREE) fill(0, R2, R1);
         fill(TW_MID, R3, R1 * R2);
+        for (int m = 0; m < 8; ++m) {
+            const long double ang = -2.0L * 3.14159265358979323846264338327950288L * m / 8;
+            t[(size_t)TW_W8 + m] = mk<T>((T)cosl(ang), (T)sinl(ang));
+        }
+        // exact zeros / ones where the long-double evaluation leaves 1e-20 residue
+        for (int m = 0; m < 8; m += 2) {
+            const int q = m / 2;    // exp(-i pi q / 2)
+            t[(size_t)TW_W8 + m] = mk<T>(T(q == 0 ? 1 : (q == 2 ? -1 : 0)), T(q == 1 ? -1 : (q == 3 ? 1 : 0)));
+        }
         return t;
     }
 
@@ -269,26 +279,19 @@ struct Fft {
 
     // ---- pruned first pass (radix 8): the butterfly `i` (= t + TPF*ii) has a single non-zero
     // input x, sitting at input index r of the butterfly.  Its outputs are x * W_8^(DIR*r*k),
-    // k = 0..7: one inexact multiply (by W_8^r), the rest are exact quarter-turn rotations and
-    // sign flips.  Writes the same slots as stepA would.
-    FCD_HD static cx<T> quarter_turns(cx<T> v, int q) {   // v * i^q
-        const cx<T> a = (q & 1) ? mk<T>(-v.y, v.x) : v;
-        return (q & 2) ? mk<T>(-a.x, -a.y) : a;
-    }
-    FCD_HD static void stepA_single(cx<T> x, int r, int ii, int t, cx<T>* s) {
+    // k = 0..7: one inexact multiply (by W_8^r), the rest are multiplications by exact 0 / +-1
+    // factors.  Writes the same slots as stepA would.
+    FCD_HD static void stepA_single(cx<T> x, int r, int ii, int t, cx<T>* s, const cx<T>* __restrict__ table) {
         static_assert(R1 == 8, "pruned first pass is written for radix 8");
-        const T h = T(0.70710678118654752440);
-        // W_8^r = exp(DIR * i * pi * r / 4)
+        const cx<T>* w8 = table + TW_W8;            // forward sign; DIR = +1 conjugates
         const int rr = r & 7;
-        const T c = (rr == 0) ? T(1) : (rr == 4) ? T(-1) : (rr == 2 || rr == 6) ? T(0) : ((rr == 1 || rr == 7) ? h : -h);
-        const T sn = (rr == 0 || rr == 4) ? T(0) : (rr == 2) ? T(1) : (rr == 6) ? T(-1) : ((rr < 4) ? h : -h);
-        const cx<T> u = mk<T>(c, DIR < 0 ? -sn : sn);
-        const int q = DIR < 0 ? ((4 - (rr & 3)) & 3) : (rr & 3);   // W_8^(2r) = (DIR*i)^r
+        cx<T> u = w8[rr], v = w8[(2 * rr) & 7];      // W_8^r and W_8^(2r) (the latter exact: 0 / +-1 entries)
+        if (DIR > 0) { u = conj(u); v = conj(v); }
+        const T sg = w8[(4 * rr) & 7].x;             // W_8^(4r) = (-1)^r
         const cx<T> x0 = x;
         const cx<T> x1 = x * u;
-        const cx<T> x2 = quarter_turns(x0, q);
-        const cx<T> x3 = quarter_turns(x1, q);
-        const T sg = (rr & 1) ? T(-1) : T(1);                      // W_8^(4r) = (-1)^r
+        const cx<T> x2 = x0 * v;
+        const cx<T> x3 = x1 * v;
         const int i = t + TPF * ii;
         cx<T>* sb = s + fft_pos(i * R1);
         sb[0] = x0; sb[1] = x1; sb[2] = x2; sb[3] = x3;
