@@ -377,8 +377,10 @@ def run_ours(args):
         achieved = alg_bytes_per_launch / (dom_ms / dom_launches * 1e-3) / 1e9
         traffic = None
         try:
-            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get(dom)
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:      # ncu --set full capture, DRAM bytes per frame
+                traffic = json.load(f)["dram_bytes_per_frame"].get(dom)
+            if traffic is not None:
+                traffic = traffic * (dom_frames / dom_launches)                   # per launch, like `achieved`
         except Exception:
             pass
         total_stage_ms = sum(v[0] for v in stages.values())
