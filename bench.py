@@ -215,7 +215,7 @@ def run_reference(args):
                              "host_cpu_count": cores},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 # --------------------------------------------------------------------------------------
@@ -233,6 +233,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # stdout carries exactly one JSON line: whatever NCCL logs (a pool-wide NCCL_DEBUG=VERSION prints
+        # "NCCL version ..." there) goes to stderr instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -404,14 +407,28 @@ def run_ours(args):
                            "calibration_factor": cal, "parallelism": f"frame-sharded x{world}, no hot-path collective"},
                 "mpix_per_s": value * P / 1e6, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu, "cufft_pipeline": cufft}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_JSON_OUT = sys.stdout
+
+
+def _reserve_stdout():
+    """stdout carries exactly ONE JSON line.  Native libraries write to fd 1 behind Python's back (NCCL prints
+    its version banner there under a pool-wide NCCL_DEBUG), so fd 1 is pointed at stderr for the rest of the
+    process and the JSON line goes to a private duplicate of the original stdout."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
 def main():
     args = parse_args()
+    _reserve_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
