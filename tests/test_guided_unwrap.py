@@ -150,3 +150,40 @@ def test_gpu_guided_unwrap_full_size():
             # every tree edge is continuous and the result is deterministic
             assert torch.equal(u, plan.unwrap_phase(w))
     plan.close()
+
+
+# ----------------------------------------------------------------------------- the reference's own example data
+def real_pair():
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_real.npz"))
+    return g, g["ref"].astype(np.float32), g["frame"].astype(np.float32), float(g["square_size"]), g["layers"].tolist()
+
+
+def test_emulated_real_camera_pair_needs_and_gets_the_guided_unwrap():
+    """examples/fcd_example.py's pair (central 512^2 crop, golden = output of the unmodified reference):
+    the wrapped phases contain residues, the scan unwrap is 20 % off, the guided unwrap matches."""
+    from tests.emul_lib import EmulPlan
+    from tests.test_emulated_kernels import bind_like_reference
+    g, ref, frm, sq, layers = real_pair()
+    plan = EmulPlan((512, 512), 1)
+    _, _, cal = bind_like_reference(plan, ref, sq, height=o.height_from_layers(layers))
+    assert cal == float(g["cal"])
+    _, w = plan.execute(frm, phases=True, unwrap=0)
+    assert plan.count_residues(w[0]) == list(g["residues"]) and min(g["residues"]) > 0
+    assert rel_l2(plan.execute(frm, unwrap=2)[0], g["height_map"]) < 1e-5
+    assert rel_l2(plan.execute(frm, unwrap=1)[0], g["height_map"]) > 0.05
+    plan.close()
+
+
+@pytest.mark.gpu
+def test_gpu_real_camera_pair_through_the_drop_in():
+    import torch
+    import fcd_b200
+    from pyfcd.fcd import fcd
+    g, ref, frm, sq, layers = real_pair()
+    hm, ph, cal = fcd.compute_height_map(ref, frm, sq, layers)              # examples/fcd_example.py:23
+    assert cal == float(g["cal"]) and hm.dtype == np.float64 and hm.flags.writeable
+    assert rel_l2(hm, g["height_map"]) < 1e-5
+    # batched API on the integer camera frames, default unwrap = "auto"
+    maps, _, _ = fcd_b200.compute_height_maps(ref, np.stack([g["frame"], g["frame"]]), sq, layers=layers)
+    assert rel_l2(maps[1].cpu().numpy(), g["height_map"]) < 1e-5 and torch.equal(maps[0], maps[1])
