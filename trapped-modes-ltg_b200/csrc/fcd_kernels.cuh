@@ -19,6 +19,7 @@
 // transform at a time (see fft_core.cuh for the natural strided ownership t + TPF*m).
 #pragma once
 #include <cmath>
+#include <cstring>
 #include "fft_core.cuh"
 
 namespace fcd {
@@ -121,6 +122,63 @@ FCD_HD void async_wait_all() {
     asm volatile("cp.async.wait_all;" ::: "memory");
 #endif
 }
+// ---- TMA (bulk async copy engine): one thread hands a contiguous global -> shared copy to the copy
+// engine, completion is signalled on an mbarrier that the consumers poll.  In the CPU emulation the
+// copy happens immediately and the barrier operations are no-ops.
+using mbar_t = unsigned long long;
+FCD_HD void mbar_init(mbar_t* bar, int count) {
+#if defined(__CUDA_ARCH__)
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#else
+    *bar = 0;
+    (void)count;
+#endif
+}
+FCD_HD void mbar_expect_tx(mbar_t* bar, unsigned bytes) {
+#if defined(__CUDA_ARCH__)
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+#else
+    (void)bar; (void)bytes;
+#endif
+}
+// size and both addresses must be multiples of 16 bytes
+FCD_HD void bulk_copy_g2s(void* smem_dst, const void* gsrc, unsigned bytes, mbar_t* bar) {
+#if defined(__CUDA_ARCH__)
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
+#else
+    std::memcpy(smem_dst, gsrc, bytes);
+    (void)bar;
+#endif
+}
+FCD_HD void mbar_wait(mbar_t* bar, unsigned parity) {
+#if defined(__CUDA_ARCH__)
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(a), "r"(parity) : "memory");
+#else
+    (void)bar; (void)parity;
+#endif
+}
+// orders this thread's earlier generic-proxy shared-memory accesses before later async-proxy (TMA) writes
+FCD_HD void fence_proxy_async() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
+
 // state the launcher maintains for kernels that prefetch the next tile (K::PIPELINED)
 struct TileLink {
     int next_bx, next_by;
@@ -224,22 +282,26 @@ struct RowFwd : AllPhases {
             // the data registers are dead from here on: fetch the next tile's rows into them
             // while this phase and the loop barrier run
             if (st.link.has_next) load_rows(p, st.link.next_bx, st.link.next_by, g, t, st.v);
+            // band extraction: lanes = G adjacent row pairs (one 16-byte store each) x consecutive band columns
             const cf* sb = reinterpret_cast<const cf*>(smem);
-            const int total = 2 * p.ncp * G;
-            for (int item = tid; item < total; item += THREADS) {
-                const int gg = item % G, cc = item / G;
-                const int i = cc / p.ncp, c = cc % p.ncp;
-                if (c >= p.nc[i]) continue;
-                const int kc = p.kc0[i] + c;
-                const int k = kc < 0 ? -kc : kc;
-                const cf x1 = sb[gg * GL::STRIDE + fft_pos(k)];
-                const cf x2 = conj(sb[gg * GL::STRIDE + fft_pos((W - k) & (W - 1))]);
-                cf a = x1 + x2;              // 2 * rowA spectrum at k
-                cf b = mul_mi(x1 - x2);      // 2 * rowB spectrum at k
-                if (kc < 0) { a = conj(a); b = conj(b); }
-                const int ya = (bx * G + gg) * 2;
-                cf2 o; o.a = a; o.b = b;
-                *reinterpret_cast<cf2*>(p.w1 + (((long long)by * 2 + i) * p.ncp + c) * p.H + ya) = o;
+            const int gg = tid % G, c0 = tid / G;
+            const int ya = (bx * G + gg) * 2;
+            const cf* sg = sb + gg * GL::STRIDE;
+            FCD_UNROLL
+            for (int i = 0; i < 2; ++i) {
+                cf* __restrict__ dst = p.w1 + ((long long)by * 2 + i) * p.ncp * p.H + ya;
+                const int nc = p.nc[i], kc0 = p.kc0[i];
+                for (int c = c0; c < nc; c += THREADS / G) {
+                    const int kc = kc0 + c;
+                    const int k = kc < 0 ? -kc : kc;
+                    const cf x1 = sg[fft_pos(k)];
+                    const cf x2 = conj(sg[fft_pos((W - k) & (W - 1))]);
+                    cf a = x1 + x2;              // 2 * rowA spectrum at k
+                    cf b = mul_mi(x1 - x2);      // 2 * rowB spectrum at k
+                    if (kc < 0) { a = conj(a); b = conj(b); }
+                    cf2 o; o.a = a; o.b = b;
+                    *reinterpret_cast<cf2*>(dst + (long long)c * p.H) = o;
+                }
             }
         }
     }
@@ -897,14 +959,35 @@ struct RowInv : AllPhases {
     using GL = GroupLayout<L, G>;
     using Params = RowInvParams;
     static constexpr bool BLOCKED_TILES = false;
-    static constexpr bool PIPELINED = false;
+    static constexpr bool PIPELINED = true;   // the next tile's two spectrum rows arrive by TMA while this tile finishes
     static constexpr int SYNC_THREADS = (L / 16 >= 32 && G > 1 && G <= 15) ? L / 16 : 0;   // per-group named barriers
     static constexpr int MIN_BLOCKS = ((G * L / 16) <= 128 ? 6 : ((G * L / 16) <= 256 ? 3 : 1));
-    static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 4;
+    static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 6;
     using TW = SmemTwiddles<FI, THREADS>;
-    static constexpr int SMEM_BYTES = TW::TW_BYTES + G * GL::STRIDE * (int)sizeof(cf);
-    FCD_HD static void prologue(const Params& p, int tid, unsigned char* smem) { TW::load(p.tw, tid, smem); }
-    struct State { cf v[16]; };
+    // The exchange buffer doubles as the TMA landing zone: row a at element 0, row b at ROW_ELEMS
+    // (W/2 + 2 elements each, a multiple of 16 bytes; w4 rows are W/2 + 4 elements apart).
+    static constexpr int ROW_ELEMS = L / 2 + 2;
+    static_assert(2 * ROW_ELEMS + 1 <= GL::STRIDE, "two spectrum rows (16-byte aligned) must fit in the exchange buffer");
+    // bulk copies need 16-byte aligned shared addresses; a group's buffer may start on an odd element
+    FCD_HD static cf* landing(cf* s, int g) { return s + ((g * GL::STRIDE) & 1); }
+    static constexpr int BAR_OFF = TW::TW_BYTES + G * GL::STRIDE * (int)sizeof(cf);
+    static constexpr int SMEM_BYTES = BAR_OFF + 16 * G;
+    FCD_HD static mbar_t* bar_of(unsigned char* smem_all, int g) { return reinterpret_cast<mbar_t*>(smem_all + BAR_OFF + 16 * g); }
+    FCD_HD static void prologue(const Params& p, int tid, unsigned char* smem) {
+        TW::load(p.tw, tid, smem);
+        if (tid < G) mbar_init(bar_of(smem, tid), 1);
+    }
+    struct State { cf v[16]; TileLink link; unsigned parity; };
+
+    FCD_HD static void stage_rows(const Params& p, int bx, int by, int g, cf* s, mbar_t* bar) {
+        const int ya = (bx * G + g) * 2;
+        const cf* ra = p.w4 + ((long long)by * p.H + ya) * p.w4p;
+        constexpr unsigned BYTES = ROW_ELEMS * (unsigned)sizeof(cf);
+        cf* land = landing(s, g);
+        mbar_expect_tx(bar, 2 * BYTES);
+        bulk_copy_g2s(land, ra, BYTES, bar);
+        bulk_copy_g2s(land + ROW_ELEMS, ra + p.w4p, BYTES, bar);
+    }
 
     template <int PH>
     FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem_all, State& st) {
@@ -912,11 +995,22 @@ struct RowInv : AllPhases {
         unsigned char* smem = smem_all + TW::TW_BYTES;
         const int g = tid / TPF, t = tid % TPF;
         cf* s = reinterpret_cast<cf*>(smem) + g * GL::STRIDE;
+        mbar_t* bar = bar_of(smem_all, g);
         const int W = L;
         const int ya = (bx * G + g) * 2;
         if constexpr (PH == 0) {
-            const cf* ra = p.w4 + ((long long)by * p.H + ya) * p.w4p;
-            const cf* rb = ra + p.w4p;
+            if (st.link.first) {
+                st.parity = 0;
+#if defined(FCD_EMULATE)
+                stage_rows(p, bx, by, g, s, bar);      // sequential emulation: every thread copies for itself (idempotent)
+#else
+                if (t == 0) stage_rows(p, bx, by, g, s, bar);
+#endif
+            }
+            mbar_wait(bar, st.parity);
+            st.parity ^= 1u;
+            const cf* ra = landing(s, g);
+            const cf* rb = ra + ROW_ELEMS;
             FCD_UNROLL
             for (int m = 0; m < 16; ++m) {
                 const int pidx = t + TPF * m;
@@ -927,13 +1021,22 @@ struct RowInv : AllPhases {
                 if (!lower) { a = conj(a); b = conj(b); }
                 st.v[m] = a + mul_pi(b);
             }
-            FI::stepA(st.v, t, s);
         } else if constexpr (PH == 1) {
-            FI::stepB(st.v, t, s, tw);
+            FI::stepA(st.v, t, s);
         } else if constexpr (PH == 2) {
+            FI::stepB(st.v, t, s, tw);
+        } else if constexpr (PH == 3) {
             FI::stepC(st.v, t, s);
+        } else if constexpr (PH == 4) {
+            FI::template gather<FI::R3, FI::R1 * FI::R2>(st.v, t, s, tw);
         } else {
-            FI::stepD(st.v, t, s, tw);
+            // every thread of the group has taken its last values out of the exchange buffer: hand it to
+            // the copy engine for the next tile, then finish this one out of registers
+            if (st.link.has_next && t == 0) {
+                fence_proxy_async();
+                stage_rows(p, st.link.next_bx, st.link.next_by, g, s, bar);
+            }
+            FI::template butterflies<FI::R3>(st.v);
             float* oa = p.height + ((long long)by * p.H + ya) * W;
             float* ob = oa + W;
             if (p.mask) {
