@@ -329,14 +329,38 @@ struct ColBand : AllPhases {
     using GL = GroupLayout<L, G>;
     using Params = ColBandParams;
     static constexpr bool BLOCKED_TILES = false;
-    static constexpr bool PIPELINED = false;
+    static constexpr bool PIPELINED = true;   // the next tile's columns arrive by TMA while this tile finishes
     static constexpr int SYNC_THREADS = 0;   // 0: block-wide barrier
     static constexpr int MIN_BLOCKS = ((G * L / 16) <= 256 ? 2 : 1);
-    static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 8;
+    static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 10;
     using TW = SmemTwiddles<FF, THREADS>;
-    static constexpr int SMEM_BYTES = TW::TW_BYTES + G * GL::STRIDE * (int)sizeof(cf);
-    FCD_HD static void prologue(const Params& p, int tid, unsigned char* smem) { TW::load(p.tw, tid, smem); }
-    struct State { cf v[16]; };
+    static_assert(L + 1 <= GL::STRIDE, "a column (16-byte aligned) must fit in the exchange buffer");
+    static constexpr int BAR_OFF = TW::TW_BYTES + G * GL::STRIDE * (int)sizeof(cf);
+    static constexpr int SMEM_BYTES = BAR_OFF + 16;
+    FCD_HD static mbar_t* bar_of(unsigned char* smem_all) { return reinterpret_cast<mbar_t*>(smem_all + BAR_OFF); }
+    FCD_HD static cf* landing(unsigned char* smem_all, int g) {
+        return reinterpret_cast<cf*>(smem_all + TW::TW_BYTES) + g * GL::STRIDE + ((g * GL::STRIDE) & 1);
+    }
+    FCD_HD static void prologue(const Params& p, int tid, unsigned char* smem) {
+        TW::load(p.tw, tid, smem);
+        if (tid == 0) mbar_init(bar_of(smem), 1);
+    }
+    struct State { cf v[16]; TileLink link; unsigned parity; };
+
+    // one thread hands the tile's (up to G) contiguous w1 columns to the copy engine; the exchange buffers
+    // are the landing zones (linear order)
+    FCD_HD static void stage_cols(const Params& p, int bx, int by, unsigned char* smem_all) {
+        const int i = by & 1;
+        constexpr unsigned BYTES = L * (unsigned)sizeof(cf);
+        int n = 0;
+        for (int g = 0; g < G; ++g) n += (bx * G + g < p.nc[i]) ? 1 : 0;
+        mbar_t* bar = bar_of(smem_all);
+        mbar_expect_tx(bar, n * BYTES);
+        for (int g = 0; g < G; ++g) {
+            const int c = bx * G + g;
+            if (c < p.nc[i]) bulk_copy_g2s(landing(smem_all, g), p.w1 + ((long long)by * p.ncp + c) * L, BYTES, bar);
+        }
+    }
 
     template <int PH>
     FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem_all, State& st) {
@@ -348,20 +372,27 @@ struct ColBand : AllPhases {
         const int i = by & 1;
         const int c = bx * G + g;
         if constexpr (PH == 0) {
-            if (c < p.nc[i]) {
-                const cf* col = p.w1 + ((long long)by * p.ncp + c) * H;
-                FCD_UNROLL
-                for (int m = 0; m < 16; ++m) st.v[m] = col[t + TPF * m];
-            } else {
-                FCD_UNROLL
-                for (int m = 0; m < 16; ++m) st.v[m] = mk<float>(0.f, 0.f);
+            if (st.link.first) {
+                st.parity = 0;
+#if defined(FCD_EMULATE)
+                stage_cols(p, bx, by, smem_all);      // sequential emulation: every thread copies for itself (idempotent)
+#else
+                if (tid == 0) stage_cols(p, bx, by, smem_all);
+#endif
             }
-            FF::stepA(st.v, t, s);
+            mbar_wait(bar_of(smem_all), st.parity);
+            st.parity ^= 1u;
+            const cf* col = landing(smem_all, g);
+            const bool valid = c < p.nc[i];
+            FCD_UNROLL
+            for (int m = 0; m < 16; ++m) st.v[m] = valid ? col[t + TPF * m] : mk<float>(0.f, 0.f);
         } else if constexpr (PH == 1) {
-            FF::stepB(st.v, t, s, tw);
+            FF::stepA(st.v, t, s);
         } else if constexpr (PH == 2) {
-            FF::stepC(st.v, t, s);
+            FF::stepB(st.v, t, s, tw);
         } else if constexpr (PH == 3) {
+            FF::stepC(st.v, t, s);
+        } else if constexpr (PH == 4) {
             FF::stepD(st.v, t, s, tw);
             int lo = 1, hi = 0;
             if (c < p.nc[i]) { lo = p.chord_lo[i * p.ncp + c]; hi = p.chord_hi[i * p.ncp + c]; }
@@ -371,14 +402,21 @@ struct ColBand : AllPhases {
                 const bool keep = (r >= lo) && (r <= hi);
                 st.v[m] = keep ? scale(st.v[m], p.scale) : mk<float>(0.f, 0.f);
             }
-        } else if constexpr (PH == 4) {
-            FI::stepA(st.v, t, s);
         } else if constexpr (PH == 5) {
-            FI::stepB(st.v, t, s, tw);
+            FI::stepA(st.v, t, s);
         } else if constexpr (PH == 6) {
+            FI::stepB(st.v, t, s, tw);
+        } else if constexpr (PH == 7) {
             FI::stepC(st.v, t, s);
+        } else if constexpr (PH == 8) {
+            FI::template gather<FI::R3, FI::R1 * FI::R2>(st.v, t, s, tw);
         } else {
-            FI::stepD(st.v, t, s, tw);
+            // the exchange buffers are idle from here on: hand them to the copy engine for the next tile
+            if (st.link.has_next && tid == 0) {
+                fence_proxy_async();
+                stage_cols(p, st.link.next_bx, st.link.next_by, smem_all);
+            }
+            FI::template butterflies<FI::R3>(st.v);
             if (c < p.nc[i]) {   // lanes: G adjacent columns x 32/G adjacent rows -> full sectors
                 cf* o = p.w2 + (long long)by * H * p.ncp + c;
                 FCD_UNROLL
