@@ -1074,19 +1074,30 @@ struct RowInv : AllPhases {
                 fence_proxy_async();
                 stage_rows(p, st.link.next_bx, st.link.next_by, g, s, bar);
             }
-            FI::template butterflies<FI::R3>(st.v);
             float* oa = p.height + ((long long)by * p.H + ya) * W;
             float* ob = oa + W;
             if (p.mask) {
+                // the mask bytes are requested before the last butterflies so that their latency hides behind the
+                // arithmetic; they are folded into two bit sets as they arrive
                 const uint8_t* ma = p.mask + (long long)by * p.mask_stride + (long long)ya * W;
                 const uint8_t* mb = ma + W;
+                unsigned keep_a = 0, keep_b = 0;
+                FCD_UNROLL
+                for (int m = 0; m < 16; ++m) {
+                    keep_a |= (ma[t + TPF * m] ? 0u : 1u) << m;
+                    keep_b |= (mb[t + TPF * m] ? 0u : 1u) << m;
+                }
+                FI::template butterflies<FI::R3>(st.v);
                 FCD_UNROLL
                 for (int m = 0; m < 16; ++m) {
                     const int x = t + TPF * m;
-                    oa[x] = ma[x] ? 0.f : st.v[m].x;
-                    ob[x] = mb[x] ? 0.f : st.v[m].y;
+                    oa[x] = ((keep_a >> m) & 1u) ? st.v[m].x : 0.f;
+                    ob[x] = ((keep_b >> m) & 1u) ? st.v[m].y : 0.f;
                 }
-            } else {
+                return;
+            }
+            FI::template butterflies<FI::R3>(st.v);
+            {
                 FCD_UNROLL
                 for (int m = 0; m < 16; ++m) {
                     oa[t + TPF * m] = st.v[m].x;

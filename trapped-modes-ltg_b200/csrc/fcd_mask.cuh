@@ -153,39 +153,60 @@ FCD_HD void uf_unite(int* L, int a, int b) {
     }
 }
 
+// LabelFlatten walks a line in segments of kLabelSeg pixels, one thread each (a whole line per thread
+// leaves the device mostly idle).
+constexpr int kLabelSeg = 64;
+
 struct LabelInitParams {
     const float* smooth;      // mode 0: foreground = smooth < sum[frame] / n
     const float* sums;        // [frames] pairwise float32 sums
     const uint8_t* mask;      // mode 1: foreground = !mask
     int* L;                   // [frames][n]: start index of the pixel's horizontal run, or -1
-    long long n_rows;         // frames * H
+    long long n_rows;         // frames * H lines, one warp each (32 * n_rows threads)
     int H, W;
     int mode;
 };
 // Run-based labelling: every foreground pixel starts out labelled with the first pixel of its
-// horizontal run, so only vertical / diagonal links between runs remain to be merged.
+// horizontal run, so only vertical / diagonal links between runs remain to be merged.  One warp per
+// line: 32 consecutive pixels per step (coalesced), the run start inside the word from a ballot, the
+// start of a run that began in an earlier word carried along in a warp-uniform register.
 struct LabelInit : ElemBase {
     using Params = LabelInitParams;
+    FCD_HD static bool fg_at(const Params& p, long long o, int c, float thr) {
+        return p.mode == 0 ? (p.smooth[o + c] < thr) : (p.mask[o + c] == 0);
+    }
     template <int PH>
     FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
-        const long long row = (long long)bx * THREADS + tid;
-        if (row >= p.n_rows) return;
+        const long long item = (long long)bx * THREADS + tid;
+        const long long row = item / 32;
+        const int lane = (int)(item % 32);
+        if (row >= p.n_rows) return;               // whole warps: THREADS is a multiple of 32
         const long long f = row / p.H;
         const int r = (int)(row % p.H);
         const int n = p.H * p.W;
         const long long o = f * n + (long long)r * p.W;
         const float thr = p.mode == 0 ? p.sums[f] / (float)n : 0.f;   // np.mean: float32 sum / count
-        int start = -1;
-        for (int c = 0; c < p.W; ++c) {
-            const bool fg = p.mode == 0 ? (p.smooth[o + c] < thr) : (p.mask[o + c] == 0);
-            if (fg) {
-                if (start < 0) start = r * p.W + c;
-                p.L[o + c] = start;
-            } else {
-                start = -1;
-                p.L[o + c] = -1;
-            }
+#if defined(__CUDA_ARCH__)
+        int carry = -1;                             // start column of the run that reaches the previous word's end
+        for (int c0 = 0; c0 < p.W; c0 += 32) {
+            const bool fg = fg_at(p, o, c0 + lane, thr);
+            const unsigned bits = __ballot_sync(0xffffffffu, fg);
+            const unsigned bg_below = ~bits & ((1u << lane) - 1u);          // background pixels to the left, in this word
+            const int start = bg_below ? c0 + (32 - __clz(bg_below)) : (carry >= 0 ? carry : c0);
+            p.L[o + c0 + lane] = fg ? r * p.W + start : -1;
+            const unsigned bg_all = ~bits;
+            carry = (bits >> 31) ? (bg_all ? c0 + (32 - __clz(bg_all)) : (carry >= 0 ? carry : c0)) : -1;
         }
+#else
+        for (int c = lane; c < p.W; c += 32) {      // the emulated thread finds its run start on its own
+            int start = -1;
+            if (fg_at(p, o, c, thr)) {
+                start = c;
+                while (start > 0 && fg_at(p, o, start - 1, thr)) --start;
+            }
+            p.L[o + c] = start < 0 ? -1 : r * p.W + start;
+        }
+#endif
     }
 };
 struct LabelMergeParams {
@@ -258,7 +279,7 @@ struct RegionStats {
 struct LabelFlattenParams {
     int* L;
     RegionStats st;
-    long long n_rows;       // frames * H
+    long long n_rows;       // frames * H * (W / kLabelSeg): one thread per line segment
     int H, W;
     int with_bbox;
 };
@@ -278,8 +299,11 @@ struct LabelFlatten : ElemBase {
     }
     template <int PH>
     FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
-        const long long row = (long long)bx * THREADS + tid;
-        if (row >= p.n_rows) return;
+        const long long item = (long long)bx * THREADS + tid;
+        if (item >= p.n_rows) return;
+        const int segs = p.W / kLabelSeg;
+        const long long row = item / segs;
+        const int cbeg = (int)(item % segs) * kLabelSeg;
         const int n = p.H * p.W;
         const long long fo = (row / p.H) * n;
         const int r = (int)(row % p.H);
@@ -287,7 +311,7 @@ struct LabelFlatten : ElemBase {
         int cur_root = -1, cnt = 0, c0 = 0, c1 = 0;
         long long sc = 0;
         int run_label = -2, run_root = -1;
-        for (int c = 0; c < p.W; ++c) {
+        for (int c = cbeg; c < cbeg + kLabelSeg; ++c) {
             const int px = r * p.W + c;
             const int lab = L[px];
             if (lab < 0) { run_label = -2; continue; }

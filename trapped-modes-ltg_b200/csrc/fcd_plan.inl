@@ -651,15 +651,19 @@ struct PlanImpl {
 
     // ------------------------------------------------------------------ structure mask / centre ----
     // analyze.mask (pydata/analyze.py:43-100) and analyze.center (pydata/analyze.py:104-140)
-    static constexpr int kMaskChunk = 16;
+    // frames per wave: several of these kernels run one thread per image line (the reference's running sums
+    // and raster labelling are sequential along a line), so the wave has to be wide to fill the device;
+    // capped at 2^28 pixels of workspace rows (~50 bytes per pixel)
+    int mask_chunk() const { return (int)std::max<long long>(1, std::min<long long>(64, (1LL << 28) / ((long long)H * W))); }
     rt::DevBuf<float> m_t0, m_smooth, m_ps0, m_ps1;
     rt::DevBuf<int> m_L, m_area, m_bbox, m_centers;
     rt::DevBuf<unsigned long long> m_sums, m_best;
 
     static int blocks_for(long long total) { return (int)((total + 255) / 256); }
+    long long nsegs(int nf) const { return (long long)nf * H * (W / kLabelSeg); }    // line segments of the labelling kernels
 
     void mask_workspace(bool with_stats) {
-        const size_t n = (size_t)H * W, c = kMaskChunk;
+        const size_t n = (size_t)H * W, c = (size_t)mask_chunk();
         m_L.alloc(c * n);
         m_area.alloc(c * n);
         m_best.alloc(c);
@@ -679,8 +683,8 @@ struct PlanImpl {
         if (smoothed < 1 || smoothed > std::min(H, W)) rt::fail("smoothed must be in [1, min(rows, cols)]");
         mask_workspace(false);
         const long long n = (long long)H * W;
-        for (int f0 = 0; f0 < n_frames; f0 += kMaskChunk) {
-            const int nf = std::min(kMaskChunk, n_frames - f0);
+        for (int f0 = 0; f0 < n_frames; f0 += mask_chunk()) {
+            const int nf = std::min(mask_chunk(), n_frames - f0);
             const long long total = nf * n;
             const float* in = frames + f0 * n;
             launch<BoxLines>(blocks_for((long long)nf * W), 1, s, BoxLinesParams{in, m_t0.ptr, H, W, smoothed, 0, (long long)nf * W});
@@ -695,12 +699,12 @@ struct PlanImpl {
                 launch<PairTree>(blocks_for(nf * m), 1, s, PairTreeParams{a, b, nf * m});
                 std::swap(a, b);
             }
-            launch<LabelInit>(blocks_for((long long)nf * H), 1, s, LabelInitParams{m_smooth.ptr, a, nullptr, m_L.ptr, (long long)nf * H, H, W, 0});
+            launch<LabelInit>(blocks_for(32LL * nf * H), 1, s, LabelInitParams{m_smooth.ptr, a, nullptr, m_L.ptr, (long long)nf * H, H, W, 0});
             launch<LabelMerge>(blocks_for(total), 1, s, LabelMergeParams{m_L.ptr, total, H, W});
             rt::dmemset(m_area.ptr, 0, sizeof(int) * (size_t)total, s);
             rt::dmemset(m_best.ptr, 0, sizeof(unsigned long long) * (size_t)nf, s);
             RegionStats st{m_area.ptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-            launch<LabelFlatten>(blocks_for((long long)nf * H), 1, s, LabelFlattenParams{m_L.ptr, st, (long long)nf * H, H, W, 0});
+            launch<LabelFlatten>(blocks_for(nsegs(nf)), 1, s, LabelFlattenParams{m_L.ptr, st, nsegs(nf), H, W, 0});
             launch<LargestRegion>(blocks_for(total), 1, s, LargestParams{m_L.ptr, st, m_best.ptr, total, H, W, 0});
             launch<MaskOut>(blocks_for(total), 1, s, MaskOutParams{m_L.ptr, m_best.ptr, mask_out + f0 * n, total, (int)n});
         }
@@ -709,10 +713,10 @@ struct PlanImpl {
     void mask_center(const uint8_t* mask, int n_frames, int* centers_host, rt::stream_t s) {
         mask_workspace(true);
         const long long n = (long long)H * W;
-        for (int f0 = 0; f0 < n_frames; f0 += kMaskChunk) {
-            const int nf = std::min(kMaskChunk, n_frames - f0);
+        for (int f0 = 0; f0 < n_frames; f0 += mask_chunk()) {
+            const int nf = std::min(mask_chunk(), n_frames - f0);
             const long long total = nf * n;
-            launch<LabelInit>(blocks_for((long long)nf * H), 1, s, LabelInitParams{nullptr, nullptr, mask + f0 * n, m_L.ptr, (long long)nf * H, H, W, 1});
+            launch<LabelInit>(blocks_for(32LL * nf * H), 1, s, LabelInitParams{nullptr, nullptr, mask + f0 * n, m_L.ptr, (long long)nf * H, H, W, 1});
             launch<LabelMerge>(blocks_for(total), 1, s, LabelMergeParams{m_L.ptr, total, H, W});
             rt::dmemset(m_area.ptr, 0, sizeof(int) * (size_t)total, s);
             rt::dmemset(m_sums.ptr, 0, sizeof(unsigned long long) * 2 * (size_t)total, s);
@@ -723,7 +727,7 @@ struct PlanImpl {
             launch<FillI32>(blocks_for(total), 1, s, FillI32Params{maxr, -1, total});
             launch<FillI32>(blocks_for(total), 1, s, FillI32Params{maxc, -1, total});
             RegionStats st{m_area.ptr, minr, maxr, minc, maxc, m_sums.ptr, m_sums.ptr + total};
-            launch<LabelFlatten>(blocks_for((long long)nf * H), 1, s, LabelFlattenParams{m_L.ptr, st, (long long)nf * H, H, W, 1});
+            launch<LabelFlatten>(blocks_for(nsegs(nf)), 1, s, LabelFlattenParams{m_L.ptr, st, nsegs(nf), H, W, 1});
             launch<LargestRegion>(blocks_for(total), 1, s, LargestParams{m_L.ptr, st, m_best.ptr, total, H, W, 1});
             launch<CenterOut>(blocks_for(nf), 1, s, CenterOutParams{m_best.ptr, st, m_centers.ptr, nf, (int)n});
             rt::d2h(centers_host + 2 * f0, m_centers.ptr, sizeof(int) * 2 * (size_t)nf, s);
