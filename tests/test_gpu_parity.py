@@ -155,6 +155,34 @@ def test_full_size_2048_properties(api):
     plan.close()
 
 
+def test_full_size_4096_properties(api):
+    """BASELINE.json configs[2] shape (4096^2; the non-pruned demodulation kernel and the 16x16x16 radix
+    plan): size-independent properties only -- carrier pixels, zero mean, reference -> flat, batch
+    invariance, linearity in 1/height, agreement with the analytic surface, guided == scan without residues."""
+    torch = api["torch"]
+    n = 4096
+    ref, frames, truth = o.synthetic_frames(n, 2)
+    sq = o.board_square_size(n)
+    plan = api["eng"].HeightMapPlan((n, n), 2)
+    cal = plan.bind(ref, square_size=sq, height=1.0)
+    assert cal == 1.0
+    assert [p.tolist() for p in plan.peaks] == [[2048 + 228, 2048 + 252], [2048 - 252, 2048 + 228]]
+    batch = torch.from_numpy(np.concatenate([frames, ref[None], frames[:1]])).cuda()
+    hm_t = plan.execute(batch)
+    hm = hm_t.cpu().numpy()
+    assert np.array_equal(hm[0], hm[3])
+    assert np.abs(hm[2]).max() < 1e-4 * np.abs(hm[0]).max()
+    for i in range(2):
+        assert abs(hm[i].mean()) < 1e-5 * np.abs(hm[i]).max()
+        t = truth[i] - truth[i].mean()
+        assert rel_l2(hm[i], t) < 0.05
+    plan.set_height(height=0.5)
+    assert rel_l2(plan.execute(batch[:1]).cpu().numpy(), hm[:1] * 2) < 1e-6
+    plan.set_height(height=1.0)
+    assert rel_l2(plan.execute(batch[:1], unwrap="herraez").cpu().numpy(), hm[:1]) < 1e-5
+    plan.close()
+
+
 def test_mask_workflow(api, golden):
     g = lambda k: golden[f"synth256_small.{k}"]
     torch = api["torch"]
