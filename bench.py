@@ -346,6 +346,27 @@ def run_ours(args):
                "frames_per_step": E, "steps": args.e2e_steps,
                "api": f"fcd_b200.HeightMapPlan.execute on pinned host buffers, {c}-frame chunks, copy/compute overlap"}
 
+        # the bound of this leg: the same host<->device copies with no kernels in between (both directions at once)
+        def copy_only():
+            k = 0
+            for c0 in range(0, E, c):
+                c1, b = min(E, c0 + c), k & 1
+                with torch.cuda.stream(s_in):
+                    d_in[b][: c1 - c0].copy_(h_in[c0:c1], non_blocking=True)
+                with torch.cuda.stream(s_out):
+                    h_out[c0:c1].copy_(d_out[b][: c1 - c0], non_blocking=True)
+                k += 1
+            torch.cuda.synchronize()
+
+        copy_only()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            copy_only()
+        dtc = time.perf_counter() - t0
+        e2e["copy_only_frames_per_s"] = E * args.e2e_steps / dtc
+        e2e["copy_only_gbs_each_way"] = E * args.e2e_steps * P * 4 / dtc / 1e9
+        e2e["frac_of_copy_bound"] = e2e["value"] / world / e2e["copy_only_frames_per_s"]
+
     # ---- the same pipeline on cuFFT (torch.fft) for comparison, bounded sample, rank 0 --------
     cufft = None
     if rank == 0 and not args.no_cufft:
