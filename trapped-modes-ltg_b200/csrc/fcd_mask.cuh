@@ -17,6 +17,16 @@
 
 namespace fcd {
 
+// H, W (and so n = H*W) are powers of two (plan constraint): pixel indices decompose with masks and
+// shifts; a 64-bit division by a runtime value per pixel costs more than the rest of these kernels
+FCD_HD int ilog2_pow2(int v) {
+#if defined(__CUDA_ARCH__)
+    return __ffs(v) - 1;
+#else
+    return __builtin_ctz((unsigned)v);
+#endif
+}
+
 struct ElemBase : NoPrologue {
     static constexpr bool BLOCKED_TILES = false;
     static constexpr bool PIPELINED = false;
@@ -178,13 +188,13 @@ struct LabelInit : ElemBase {
     template <int PH>
     FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
         const long long item = (long long)bx * THREADS + tid;
-        const long long row = item / 32;
-        const int lane = (int)(item % 32);
+        const long long row = item >> 5;
+        const int lane = (int)(item & 31);
         if (row >= p.n_rows) return;               // whole warps: THREADS is a multiple of 32
-        const long long f = row / p.H;
-        const int r = (int)(row % p.H);
+        const long long f = row >> ilog2_pow2(p.H);
+        const int r = (int)(row & (p.H - 1));
         const int n = p.H * p.W;
-        const long long o = f * n + (long long)r * p.W;
+        const long long o = row * p.W;
         const float thr = p.mode == 0 ? p.sums[f] / (float)n : 0.f;   // np.mean: float32 sum / count
 #if defined(__CUDA_ARCH__)
         int carry = -1;                             // start column of the run that reaches the previous word's end
@@ -222,10 +232,10 @@ struct LabelMerge : ElemBase {
         const long long i = (long long)bx * THREADS + tid;
         if (i >= p.total) return;
         const int n = p.H * p.W;
-        int* L = p.L + (i / n) * n;
-        const int px = (int)(i % n);
+        int* L = p.L + (i & ~(long long)(n - 1));
+        const int px = (int)(i & (n - 1));
         if (L[px] < 0) return;
-        const int r = px / p.W, c = px % p.W;
+        const int r = px >> ilog2_pow2(p.W), c = px & (p.W - 1);
         if (r == 0) return;
         const bool w = c > 0 && L[px - 1] >= 0;
         const bool e = c + 1 < p.W && L[px + 1] >= 0;
@@ -276,6 +286,31 @@ struct RegionStats {
     int* minr; int* maxr; int* minc; int* maxc;     // initialised to +big / -1 (only with bbox)
     unsigned long long* sumr; unsigned long long* sumc;
 };
+// The statistics arrays are indexed by root pixel and only roots are ever touched: initialise just those
+// entries (one read of L) instead of filling 48 bytes per pixel.
+struct RootStatsInitParams {
+    const int* L;
+    RegionStats st;
+    long long total;
+    int n;
+    int with_bbox;
+};
+struct RootStatsInit : ElemBase {
+    using Params = RootStatsInitParams;
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
+        const long long i = (long long)bx * THREADS + tid;
+        if (i >= p.total) return;
+        if (p.L[i] != (int)(i & (p.n - 1))) return;           // not a root
+        p.st.area[i] = 0;
+        if (p.with_bbox) {
+            p.st.minr[i] = 0x7fffffff; p.st.minc[i] = 0x7fffffff;
+            p.st.maxr[i] = -1; p.st.maxc[i] = -1;
+            p.st.sumr[i] = 0ull; p.st.sumc[i] = 0ull;
+        }
+    }
+};
+
 struct LabelFlattenParams {
     int* L;
     RegionStats st;
@@ -301,12 +336,12 @@ struct LabelFlatten : ElemBase {
     FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
         const long long item = (long long)bx * THREADS + tid;
         if (item >= p.n_rows) return;
-        const int segs = p.W / kLabelSeg;
-        const long long row = item / segs;
-        const int cbeg = (int)(item % segs) * kLabelSeg;
+        const int segs = p.W / kLabelSeg;                       // a power of two
+        const long long row = item >> ilog2_pow2(segs);
+        const int cbeg = (int)(item & (segs - 1)) * kLabelSeg;
         const int n = p.H * p.W;
-        const long long fo = (row / p.H) * n;
-        const int r = (int)(row % p.H);
+        const long long fo = (row >> ilog2_pow2(p.H)) * n;
+        const int r = (int)(row & (p.H - 1));
         int* L = p.L + fo;
         int cur_root = -1, cnt = 0, c0 = 0, c1 = 0;
         long long sc = 0;
@@ -348,8 +383,8 @@ struct LargestRegion : ElemBase {
         const long long i = (long long)bx * THREADS + tid;
         if (i >= p.total) return;
         const int n = p.H * p.W;
-        const long long f = i / n, fo = f * n;
-        const int px = (int)(i % n);
+        const long long f = i >> ilog2_pow2(n), fo = i & ~(long long)(n - 1);
+        const int px = (int)(i & (n - 1));
         if (p.L[i] != px) return;                       // not a root
         if (p.holes_only) {
             const bool inside = p.st.minr[fo + px] > 0 && p.st.minc[fo + px] > 0 &&
@@ -375,7 +410,7 @@ struct MaskOut : ElemBase {
     FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
         const long long i = (long long)bx * THREADS + tid;
         if (i >= p.total) return;
-        const unsigned long long key = p.best[i / p.n];
+        const unsigned long long key = p.best[i >> ilog2_pow2(p.n)];
         const int root = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
         p.mask[i] = (key != 0ull && p.L[i] == root) ? 1 : 0;
     }

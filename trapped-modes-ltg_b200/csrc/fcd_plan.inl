@@ -701,9 +701,9 @@ struct PlanImpl {
             }
             launch<LabelInit>(blocks_for(32LL * nf * H), 1, s, LabelInitParams{m_smooth.ptr, a, nullptr, m_L.ptr, (long long)nf * H, H, W, 0});
             launch<LabelMerge>(blocks_for(total), 1, s, LabelMergeParams{m_L.ptr, total, H, W});
-            rt::dmemset(m_area.ptr, 0, sizeof(int) * (size_t)total, s);
             rt::dmemset(m_best.ptr, 0, sizeof(unsigned long long) * (size_t)nf, s);
             RegionStats st{m_area.ptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+            launch<RootStatsInit>(blocks_for(total), 1, s, RootStatsInitParams{m_L.ptr, st, total, (int)n, 0});
             launch<LabelFlatten>(blocks_for(nsegs(nf)), 1, s, LabelFlattenParams{m_L.ptr, st, nsegs(nf), H, W, 0});
             launch<LargestRegion>(blocks_for(total), 1, s, LargestParams{m_L.ptr, st, m_best.ptr, total, H, W, 0});
             launch<MaskOut>(blocks_for(total), 1, s, MaskOutParams{m_L.ptr, m_best.ptr, mask_out + f0 * n, total, (int)n});
@@ -718,15 +718,10 @@ struct PlanImpl {
             const long long total = nf * n;
             launch<LabelInit>(blocks_for(32LL * nf * H), 1, s, LabelInitParams{nullptr, nullptr, mask + f0 * n, m_L.ptr, (long long)nf * H, H, W, 1});
             launch<LabelMerge>(blocks_for(total), 1, s, LabelMergeParams{m_L.ptr, total, H, W});
-            rt::dmemset(m_area.ptr, 0, sizeof(int) * (size_t)total, s);
-            rt::dmemset(m_sums.ptr, 0, sizeof(unsigned long long) * 2 * (size_t)total, s);
             rt::dmemset(m_best.ptr, 0, sizeof(unsigned long long) * (size_t)nf, s);
             int* minr = m_bbox.ptr; int* maxr = minr + total; int* minc = maxr + total; int* maxc = minc + total;
-            launch<FillI32>(blocks_for(total), 1, s, FillI32Params{minr, 0x7fffffff, total});
-            launch<FillI32>(blocks_for(total), 1, s, FillI32Params{minc, 0x7fffffff, total});
-            launch<FillI32>(blocks_for(total), 1, s, FillI32Params{maxr, -1, total});
-            launch<FillI32>(blocks_for(total), 1, s, FillI32Params{maxc, -1, total});
             RegionStats st{m_area.ptr, minr, maxr, minc, maxc, m_sums.ptr, m_sums.ptr + total};
+            launch<RootStatsInit>(blocks_for(total), 1, s, RootStatsInitParams{m_L.ptr, st, total, (int)n, 1});
             launch<LabelFlatten>(blocks_for(nsegs(nf)), 1, s, LabelFlattenParams{m_L.ptr, st, nsegs(nf), H, W, 1});
             launch<LargestRegion>(blocks_for(total), 1, s, LargestParams{m_L.ptr, st, m_best.ptr, total, H, W, 1});
             launch<CenterOut>(blocks_for(nf), 1, s, CenterOutParams{m_best.ptr, st, m_centers.ptr, nf, (int)n});
