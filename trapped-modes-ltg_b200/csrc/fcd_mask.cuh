@@ -97,6 +97,88 @@ struct BoxLines : ElemBase {
     }
 };
 
+// ---- box filter along the rows (axis 1), window <= 32: one warp per 32 rows --------------------------------
+// A thread per row (BoxLines) walks 32 different cache lines per warp step.  Here the warp moves 32 x 32
+// tiles through shared memory instead: rows are loaded and stored 128 contiguous bytes at a time, lane l then
+// runs row l's sequential float64 recurrence (exactly BoxLines' operation order) out of the tile ring.
+struct BoxRowsWarp : NoPrologue {
+    using Params = BoxLinesParams;      // axis is 1; n_lines = frames * H (a multiple of 32)
+    static constexpr bool BLOCKED_TILES = false;
+    static constexpr bool PIPELINED = false;
+    static constexpr int SYNC_THREADS = 0;
+    static constexpr int MIN_BLOCKS = 1;
+    static constexpr int THREADS = 128, PHASES = 1;
+    static constexpr int TILE = 32 * 33;                                   // padded 32 x 32 floats
+    static constexpr int SMEM_BYTES = (THREADS / 32) * 4 * TILE * (int)sizeof(float);   // ring of 3 + output tile per warp
+    struct State { int dummy; };
+
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem, State&) {
+        const long long wid = (long long)bx * (THREADS / 32) + tid / 32;  // global warp = block of 32 rows
+        const int lane = tid % 32;
+        if (wid * 32 >= p.n_lines) return;
+        const int n = p.W;
+        const int s1 = p.size / 2, s2 = p.size - s1 - 1;
+        const double dsize = (double)p.size;
+#if defined(__CUDA_ARCH__)
+        const float* __restrict__ a = p.in + wid * 32 * n;                // 32 consecutive rows (same frame: H % 32 == 0)
+        float* __restrict__ o = p.out + wid * 32 * n;
+        float* T = reinterpret_cast<float*>(smem) + (tid / 32) * 4 * TILE;
+        float* O = T + 3 * TILE;
+        const int ntiles = n / 32;
+        auto load_tile = [&](int k) {
+            float* t = T + (k % 3) * TILE;
+            FCD_UNROLL
+            for (int rr = 0; rr < 32; ++rr) t[rr * 33 + lane] = a[(long long)rr * n + 32 * k + lane];
+        };
+        auto at = [&](int j) -> double {           // 'reflect', then this lane's row out of the ring
+            if (j < 0) j = -j - 1;
+            if (j >= n) j = 2 * n - 1 - j;
+            return (double)T[((j >> 5) % 3) * TILE + lane * 33 + (j & 31)];
+        };
+        load_tile(0);
+        if (ntiles > 1) load_tile(1);
+        __syncwarp();
+        double tmp = 0.0;
+        for (int l = 0; l < p.size; ++l) tmp += at(l - s1);
+        for (int k = 0; k < ntiles; ++k) {
+            for (int cc = 0; cc < 32; ++cc) {
+                const int l = 32 * k + cc;
+                if (l > 0) {
+                    const double d = at(l + s2) - at(l - 1 - s1);
+                    tmp += d;
+                }
+                O[lane * 33 + cc] = (float)(tmp / dsize);
+            }
+            __syncwarp();
+            FCD_UNROLL
+            for (int rr = 0; rr < 32; ++rr) o[(long long)rr * n + 32 * k + lane] = O[rr * 33 + lane];
+            if (k + 2 < ntiles) load_tile(k + 2);          // replaces tile k - 1, which no later column reads
+            __syncwarp();
+        }
+#else
+        // sequential emulation: the same recurrence, one row per emulated thread
+        const float* __restrict__ a = p.in + (wid * 32 + lane) * n;
+        float* __restrict__ o = p.out + (wid * 32 + lane) * n;
+        auto at = [&](int j) -> double {
+            if (j < 0) j = -j - 1;
+            if (j >= n) j = 2 * n - 1 - j;
+            return (double)a[j];
+        };
+        double tmp = 0.0;
+        for (int l = 0; l < p.size; ++l) tmp += at(l - s1);
+        for (int l = 0; l < n; ++l) {
+            if (l > 0) {
+                const double d = at(l + s2) - at(l - 1 - s1);
+                tmp += d;
+            }
+            o[l] = (float)(tmp / dsize);
+        }
+        (void)smem;
+#endif
+    }
+};
+
 // ---- np.mean(float32): block sums of 128 with eight accumulators, then a binary tree ------
 FCD_HD float fadd_rn(float a, float b) {
 #if defined(__CUDA_ARCH__)

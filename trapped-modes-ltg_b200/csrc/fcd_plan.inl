@@ -688,7 +688,10 @@ struct PlanImpl {
             const long long total = nf * n;
             const float* in = frames + f0 * n;
             launch<BoxLines>(blocks_for((long long)nf * W), 1, s, BoxLinesParams{in, m_t0.ptr, H, W, smoothed, 0, (long long)nf * W});
-            launch<BoxLines>(blocks_for((long long)nf * H), 1, s, BoxLinesParams{m_t0.ptr, m_smooth.ptr, H, W, smoothed, 1, (long long)nf * H});
+            if (smoothed <= 32)     // warp-tiled rows: coalesced, same arithmetic
+                launch<BoxRowsWarp>((int)(((long long)nf * H / 32 + 3) / 4), 1, s, BoxLinesParams{m_t0.ptr, m_smooth.ptr, H, W, smoothed, 1, (long long)nf * H});
+            else
+                launch<BoxLines>(blocks_for((long long)nf * H), 1, s, BoxLinesParams{m_t0.ptr, m_smooth.ptr, H, W, smoothed, 1, (long long)nf * H});
             // np.mean(smooth): float32 pairwise sum
             long long m = n / 128;
             launch<PairBlockSum>(blocks_for(nf * m), 1, s, PairBlockParams{m_smooth.ptr, m_ps0.ptr, nf * m});
