@@ -193,19 +193,36 @@ struct PairBlockParams {
     float* out;          // [frames][n / 128]
     long long n_blocks;  // frames * n / 128
 };
+// Eight lanes per 128-element block, lane k owning numpy's accumulator r[k] (elements k, k+8, ...): a warp
+// step reads four full 32-byte sectors instead of 32 scattered words, and the final
+// ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) is three butterfly shuffles (float addition is commutative, so
+// every lane of a pair holds the same partial sum).  n_threads = 8 * n_blocks.
 struct PairBlockSum : ElemBase {
     using Params = PairBlockParams;
     template <int PH>
     FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
-        const long long b = (long long)bx * THREADS + tid;
-        if (b >= p.n_blocks) return;
+        const long long item = (long long)bx * THREADS + tid;
+        const long long b = item >> 3;
+        const int k = (int)(item & 7);
+        if (b >= p.n_blocks) return;                 // n_blocks is a multiple of 4: whole warps leave together
         const float* __restrict__ a = p.in + b * 128;
+#if defined(__CUDA_ARCH__)
+        float r = a[k];
+        FCD_UNROLL
+        for (int i = 8; i < 128; i += 8) r = fadd_rn(r, a[i + k]);
+        r = fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+        r = fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+        r = fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
+        if (k == 0) p.out[b] = r;
+#else
+        if (k != 0) return;                          // sequential emulation: one thread does the block
         float r[8];
-        for (int k = 0; k < 8; ++k) r[k] = a[k];
+        for (int q = 0; q < 8; ++q) r[q] = a[q];
         for (int i = 8; i < 128; i += 8)
-            for (int k = 0; k < 8; ++k) r[k] = fadd_rn(r[k], a[i + k]);
+            for (int q = 0; q < 8; ++q) r[q] = fadd_rn(r[q], a[i + q]);
         p.out[b] = fadd_rn(fadd_rn(fadd_rn(r[0], r[1]), fadd_rn(r[2], r[3])),
                            fadd_rn(fadd_rn(r[4], r[5]), fadd_rn(r[6], r[7])));
+#endif
     }
 };
 struct PairTreeParams {

@@ -694,7 +694,7 @@ struct PlanImpl {
                 launch<BoxLines>(blocks_for((long long)nf * H), 1, s, BoxLinesParams{m_t0.ptr, m_smooth.ptr, H, W, smoothed, 1, (long long)nf * H});
             // np.mean(smooth): float32 pairwise sum
             long long m = n / 128;
-            launch<PairBlockSum>(blocks_for(nf * m), 1, s, PairBlockParams{m_smooth.ptr, m_ps0.ptr, nf * m});
+            launch<PairBlockSum>(blocks_for(8 * nf * m), 1, s, PairBlockParams{m_smooth.ptr, m_ps0.ptr, nf * m});
             float* a = m_ps0.ptr;
             float* b = m_ps1.ptr;
             while (m > 1) {
