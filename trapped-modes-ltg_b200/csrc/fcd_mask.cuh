@@ -271,6 +271,7 @@ struct LabelInitParams {
     const float* sums;        // [frames] pairwise float32 sums
     const uint8_t* mask;      // mode 1: foreground = !mask
     int* L;                   // [frames][n]: start index of the pixel's horizontal run, or -1
+    unsigned* bits;           // [frames][H][W/32]: foreground bit per pixel (bit i = column 32*word + i)
     long long n_rows;         // frames * H lines, one warp each (32 * n_rows threads)
     int H, W;
     int mode;
@@ -303,6 +304,7 @@ struct LabelInit : ElemBase {
             const unsigned bg_below = ~bits & ((1u << lane) - 1u);          // background pixels to the left, in this word
             const int start = bg_below ? c0 + (32 - __clz(bg_below)) : (carry >= 0 ? carry : c0);
             p.L[o + c0 + lane] = fg ? r * p.W + start : -1;
+            if (lane == 0) p.bits[(o + c0) >> 5] = bits;
             const unsigned bg_all = ~bits;
             carry = (bits >> 31) ? (bg_all ? c0 + (32 - __clz(bg_all)) : (carry >= 0 ? carry : c0)) : -1;
         }
@@ -315,38 +317,51 @@ struct LabelInit : ElemBase {
             }
             p.L[o + c] = start < 0 ? -1 : r * p.W + start;
         }
+        if (lane == 0)
+            for (int c0 = 0; c0 < p.W; c0 += 32) {
+                unsigned bits = 0;
+                for (int q = 0; q < 32; ++q) bits |= (fg_at(p, o, c0 + q, thr) ? 1u : 0u) << q;
+                p.bits[(o + c0) >> 5] = bits;
+            }
 #endif
     }
 };
 struct LabelMergeParams {
     int* L;
-    long long total;
+    const unsigned* bits;     // [frames][H][W/32] from LabelInit
+    long long total;          // frames * H * (W / 32): one thread per 32-pixel word
     int H, W;
 };
-// 8-connectivity links to the previous row, once per place where two runs first touch
+// 8-connectivity links to the previous row, once per place where two runs first touch.  Works on the
+// foreground bit words: the three "first touch" conditions are bit expressions over the word, the word
+// above and the edge bits of the four neighbouring words, and only their set bits reach the union-find.
 struct LabelMerge : ElemBase {
     using Params = LabelMergeParams;
     template <int PH>
     FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
         const long long i = (long long)bx * THREADS + tid;
         if (i >= p.total) return;
-        const int n = p.H * p.W;
-        int* L = p.L + (i & ~(long long)(n - 1));
-        const int px = (int)(i & (n - 1));
-        if (L[px] < 0) return;
-        const int r = px >> ilog2_pow2(p.W), c = px & (p.W - 1);
+        const int wpr = p.W >> 5;                                   // words per row (a power of two)
+        const int wc = (int)(i & (wpr - 1));
+        const long long row = i >> ilog2_pow2(wpr);
+        const int r = (int)(row & (p.H - 1));
         if (r == 0) return;
-        const bool w = c > 0 && L[px - 1] >= 0;
-        const bool e = c + 1 < p.W && L[px + 1] >= 0;
-        const bool nn = L[px - p.W] >= 0;
-        const bool nw = c > 0 && L[px - p.W - 1] >= 0;
-        const bool ne = c + 1 < p.W && L[px - p.W + 1] >= 0;
-        if (nn) {
-            if (!w || !nw) uf_unite(L, px, px - p.W);          // first pixel of this overlap of the two runs
-        } else {
-            if (nw && !w) uf_unite(L, px, px - p.W - 1);        // diagonal touch on the left
-            if (ne && !e) uf_unite(L, px, px - p.W + 1);        // diagonal touch on the right
-        }
+        const unsigned C = p.bits[i];
+        if (C == 0u) return;
+        const unsigned N = p.bits[i - wpr];
+        const unsigned Cl = wc > 0 ? p.bits[i - 1] : 0u, Cr = wc + 1 < wpr ? p.bits[i + 1] : 0u;
+        const unsigned Nl = wc > 0 ? p.bits[i - wpr - 1] : 0u, Nr = wc + 1 < wpr ? p.bits[i - wpr + 1] : 0u;
+        const unsigned Wm = (C << 1) | (Cl >> 31), Em = (C >> 1) | (Cr << 31);       // west / east neighbour is foreground
+        const unsigned NWm = (N << 1) | (Nl >> 31), NEm = (N >> 1) | (Nr << 31);
+        unsigned up = C & N & ~(Wm & NWm);          // first pixel of an overlap with the run above
+        unsigned dl = C & ~N & NWm & ~Wm;           // diagonal touch on the left
+        unsigned dr = C & ~N & NEm & ~Em;           // diagonal touch on the right
+        const int n = p.H * p.W;
+        int* L = p.L + (row >> ilog2_pow2(p.H)) * n;
+        const int px0 = r * p.W + (wc << 5);
+        while (up) { const int q = ilog2_pow2((int)(up & (0u - up))); up &= up - 1u; uf_unite(L, px0 + q, px0 + q - p.W); }
+        while (dl) { const int q = ilog2_pow2((int)(dl & (0u - dl))); dl &= dl - 1u; uf_unite(L, px0 + q, px0 + q - p.W - 1); }
+        while (dr) { const int q = ilog2_pow2((int)(dr & (0u - dr))); dr &= dr - 1u; uf_unite(L, px0 + q, px0 + q - p.W + 1); }
     }
 };
 

@@ -657,6 +657,7 @@ struct PlanImpl {
     int mask_chunk() const { return (int)std::max<long long>(1, std::min<long long>(64, (1LL << 28) / ((long long)H * W))); }
     rt::DevBuf<float> m_t0, m_smooth, m_ps0, m_ps1;
     rt::DevBuf<int> m_L, m_area, m_bbox, m_centers;
+    rt::DevBuf<unsigned> m_bits;
     rt::DevBuf<unsigned long long> m_sums, m_best;
 
     static int blocks_for(long long total) { return (int)((total + 255) / 256); }
@@ -665,6 +666,7 @@ struct PlanImpl {
     void mask_workspace(bool with_stats) {
         const size_t n = (size_t)H * W, c = (size_t)mask_chunk();
         m_L.alloc(c * n);
+        m_bits.alloc(c * n / 32);
         m_area.alloc(c * n);
         m_best.alloc(c);
         if (with_stats) {
@@ -702,8 +704,8 @@ struct PlanImpl {
                 launch<PairTree>(blocks_for(nf * m), 1, s, PairTreeParams{a, b, nf * m});
                 std::swap(a, b);
             }
-            launch<LabelInit>(blocks_for(32LL * nf * H), 1, s, LabelInitParams{m_smooth.ptr, a, nullptr, m_L.ptr, (long long)nf * H, H, W, 0});
-            launch<LabelMerge>(blocks_for(total), 1, s, LabelMergeParams{m_L.ptr, total, H, W});
+            launch<LabelInit>(blocks_for(32LL * nf * H), 1, s, LabelInitParams{m_smooth.ptr, a, nullptr, m_L.ptr, m_bits.ptr, (long long)nf * H, H, W, 0});
+            launch<LabelMerge>(blocks_for(total / 32), 1, s, LabelMergeParams{m_L.ptr, m_bits.ptr, total / 32, H, W});
             rt::dmemset(m_best.ptr, 0, sizeof(unsigned long long) * (size_t)nf, s);
             RegionStats st{m_area.ptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
             launch<RootStatsInit>(blocks_for(total), 1, s, RootStatsInitParams{m_L.ptr, st, total, (int)n, 0});
@@ -719,8 +721,8 @@ struct PlanImpl {
         for (int f0 = 0; f0 < n_frames; f0 += mask_chunk()) {
             const int nf = std::min(mask_chunk(), n_frames - f0);
             const long long total = nf * n;
-            launch<LabelInit>(blocks_for(32LL * nf * H), 1, s, LabelInitParams{nullptr, nullptr, mask + f0 * n, m_L.ptr, (long long)nf * H, H, W, 1});
-            launch<LabelMerge>(blocks_for(total), 1, s, LabelMergeParams{m_L.ptr, total, H, W});
+            launch<LabelInit>(blocks_for(32LL * nf * H), 1, s, LabelInitParams{nullptr, nullptr, mask + f0 * n, m_L.ptr, m_bits.ptr, (long long)nf * H, H, W, 1});
+            launch<LabelMerge>(blocks_for(total / 32), 1, s, LabelMergeParams{m_L.ptr, m_bits.ptr, total / 32, H, W});
             rt::dmemset(m_best.ptr, 0, sizeof(unsigned long long) * (size_t)nf, s);
             int* minr = m_bbox.ptr; int* maxr = minr + total; int* minc = maxr + total; int* maxc = minc + total;
             RegionStats st{m_area.ptr, minr, maxr, minc, maxc, m_sums.ptr, m_sums.ptr + total};
