@@ -219,6 +219,22 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------
+def _bind_to_gpu_numa_node(index):
+    """Run this rank (and so its pinned host buffers, first-touch) on the CPUs NVML reports as local to its GPU:
+    the host<->device leg of several ranks otherwise crosses the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -232,6 +248,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    _bind_to_gpu_numa_node(local)
     if world > 1:
         # stdout carries exactly one JSON line: whatever NCCL logs (a pool-wide NCCL_DEBUG=VERSION prints
         # "NCCL version ..." there) goes to stderr instead
