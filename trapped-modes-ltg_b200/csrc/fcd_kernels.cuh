@@ -528,12 +528,12 @@ struct RowDemod {
         }
     }
     // -angle(g * ccsgn) = -wrap(angle(g) + angle(ccsgn))           (fcd.py:118)
-    FCD_HD static bool demod(const Params& p, int i, int y, int t, const cf* v, float* ph) {
-        const int W = L;
-        const float* __restrict__ th = p.theta + ((long long)i * p.H + y) * W;
-        float c[16];
+    FCD_HD static void load_theta(const Params& p, int i, int y, int t, float* c) {
+        const float* __restrict__ th = p.theta + ((long long)i * p.H + y) * L;
         FCD_UNROLL
-        for (int m = 0; m < 16; ++m) c[m] = th[t + TPF * m];     // all loads in flight first
+        for (int m = 0; m < 16; ++m) c[m] = th[t + TPF * m];
+    }
+    FCD_HD static bool demod(const float* c, const cf* v, float* ph) {
         float big = 0.f;
         FCD_UNROLL
         for (int m = 0; m < 16; ++m) {
@@ -601,10 +601,15 @@ struct RowDemod {
             FI::stepC(st.v, t, s0);
             FI::stepC(st.w, t, s1);
         } else if constexpr (PH == 3) {
+            // theta of carrier 0 is requested before the last butterflies, theta of carrier 1 before carrier 0's
+            // arctangents: each batch of loads has a long stretch of arithmetic to hide behind
+            float c0[16], c1[16];
+            load_theta(p, 0, y, t, c0);
             FI::stepD2(st.v, st.w, t, s0, s1, tw);
+            load_theta(p, 1, y, t, c1);
             float ph0[16], ph1[16];
-            const bool big0 = demod(p, 0, y, t, st.v, ph0);
-            const bool big1 = demod(p, 1, y, t, st.w, ph1);
+            const bool big0 = demod(c0, st.v, ph0);
+            const bool big1 = demod(c1, st.w, ph1);
             if (big0 || big1) *flag = 1;      // this row may contain 2*pi jumps
             FCD_UNROLL
             for (int m = 0; m < 16; ++m) st.v[m] = mk<float>(ph0[m], ph1[m]);
