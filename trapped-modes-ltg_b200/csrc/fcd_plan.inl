@@ -470,7 +470,7 @@ struct PlanImpl {
     rt::DevBuf<po_t> u_po;
     rt::DevBuf<unsigned long long> u_bw;
     rt::DevBuf<unsigned> u_be;
-    rt::DevBuf<int> u_merges;
+    rt::DevBuf<unsigned> u_counters, u_list[2], u_chosen;
     long long unwrap_rounds = 0;
 
     void unwrap_maps(const float* wrapped, int n_maps, float* out, rt::stream_t s) {
@@ -490,29 +490,49 @@ struct PlanImpl {
             u_border.upload(b, s);
         }
         const size_t cap = (size_t)kUnwrapMaps * n;
-        u_rel.alloc(cap); u_po.alloc(cap); u_bw.alloc(cap); u_be.alloc(cap); u_merges.alloc(1);
+        u_rel.alloc(cap); u_po.alloc(cap); u_bw.alloc(cap); u_be.alloc(cap); u_counters.alloc(4);
+        u_list[0].alloc(2 * cap); u_list[1].alloc(2 * cap); u_chosen.alloc(cap);
         for (int m0 = 0; m0 < n_maps; m0 += kUnwrapMaps) {
             const int nm = std::min(kUnwrapMaps, n_maps - m0);
             const long long total = nm * n;
             const float* w = wrapped + m0 * n;
             launch<MstReliability>(blocks_for(total), 1, s, MstRelParams{w, u_border.ptr, u_rel.ptr, u_po.ptr, total, H, W});
-            MstRoundParams rp{w, u_rel.ptr, u_po.ptr, u_bw.ptr, u_be.ptr, u_merges.ptr, total, H, W, nullptr};
-            MstRoundParams rp2 = rp;
-            rp2.total = 2 * total;
-            for (int round = 0; round < 64; ++round) {
-                rt::dmemset(u_merges.ptr, 0, sizeof(int), s);
-                launch<MstReset>(blocks_for(total), 1, s, rp);
-                launch<MstSelect<0>>(blocks_for(2 * total), 1, s, rp2);
-                launch<MstSelect<1>>(blocks_for(2 * total), 1, s, rp2);
-                launch<MstUnite>(blocks_for(total), 1, s, rp);
-                launch<MstFlatten>(blocks_for(total), 1, s, rp);
-                int merges = 0;
-                rt::d2h(&merges, u_merges.ptr, sizeof(int), s);
+            MstRoundParams base{w, u_rel.ptr, u_po.ptr, u_bw.ptr, u_be.ptr, nullptr, nullptr, u_counters.ptr, total, H, W, nullptr};
+            launch<MstReset>(blocks_for(total), 1, s, base);
+            const unsigned* list = nullptr;            // round 0: all 2n edges of every map, enumerated implicitly
+            long long count = 2 * total;
+            for (int round = 0; round < 64 && count > 0; ++round) {
+                rt::dmemset(u_counters.ptr, 0, 4 * sizeof(unsigned), s);
+                MstRoundParams rp = base;
+                rp.list = list; rp.count = count;
+                if (round > 0) launch<MstResetList>(blocks_for(count), 1, s, rp);
+                launch<MstSelect<0>>(blocks_for(count), 1, s, rp);
+                launch<MstSelect<1>>(blocks_for(count), 1, s, rp);
+                rp.list_out = u_chosen.ptr;
+                launch<MstMark>(blocks_for(count), 1, s, rp);
+                unsigned c[4];
+                rt::d2h(c, u_counters.ptr, sizeof(c), s);
+                const long long chosen = c[2];
+                if (chosen == 0) break;                 // no component has an outgoing edge left
+                MstRoundParams up = base;
+                up.list = u_chosen.ptr; up.count = chosen;
+                launch<MstUnite>(blocks_for(chosen), 1, s, up);
+                if (round < 2) {                        // early rounds touch most pixels: flatten everything
+                    MstRoundParams fp = base;
+                    launch<MstFlatten>(blocks_for(total), 1, s, fp);
+                }
+                unsigned* out_list = u_list[round & 1].ptr;
+                rp.list_out = out_list;
+                launch<MstCompact>(blocks_for(count), 1, s, rp);
+                rt::d2h(c, u_counters.ptr, sizeof(c), s);
                 ++unwrap_rounds;
-                if (merges == 0) break;
+                list = out_list;
+                count = c[1];
             }
-            rp.out = out + m0 * n;
-            launch<MstApply>(blocks_for(total), 1, s, rp);
+            MstRoundParams fp = base;
+            launch<MstFlatten>(blocks_for(total), 1, s, fp);
+            fp.out = out + m0 * n;
+            launch<MstApply>(blocks_for(total), 1, s, fp);
         }
     }
 

@@ -135,26 +135,65 @@ struct MstReliability : ElemBase {
     }
 };
 
-// ---- one Boruvka round ---------------------------------------------------------------------------
+// ---- Boruvka rounds over a shrinking list of cross edges -------------------------------------------------
+// Round 0 enumerates all 2n edges of every map implicitly; every later round works on the list of edges whose
+// end points still lie in different components (compacted after each round), so the work per round falls
+// with the number of component boundaries instead of staying at 2n.  A global edge id is map * 2n + e.
 struct MstRoundParams {
     const float* w;
     const double* rel;
     po_t* PO;
     unsigned long long* best_w;   // [maps][n] per root: smallest outgoing weight (bit pattern of a double >= 0)
     unsigned* best_e;             // [maps][n] per root: smallest edge index among those of that weight
-    int* merges;                  // number of successful unions in this round
-    long long total;              // maps * n (MstReset, MstUnite, MstFlatten, MstApply) or maps * 2n (select)
+    const unsigned* list;         // global edge ids of this round, or null: all edges 0 .. count-1
+    unsigned* list_out;           // MstCompact: surviving cross edges; MstMark: chosen edges
+    unsigned* counters;           // [0] merges, [1] length of list_out (MstCompact), [2] chosen (MstMark)
+    long long count;              // edges in this round (Select / Mark / Compact / ResetList), pixels (Reset, Flatten, Apply)
     int H, W;
     float* out;                   // MstApply
 };
+FCD_HD unsigned atomic_add_u32(unsigned* a, unsigned v) {
+#if defined(__CUDA_ARCH__)
+    return atomicAdd(a, v);
+#else
+    const unsigned o = *a;
+    *a += v;
+    return o;
+#endif
+}
+// (map, e, u, v) of item i of the round; false for the non-edges of the implicit enumeration
+FCD_HD bool mst_edge(const MstRoundParams& p, long long i, long long& map, int& e, int& u, int& v) {
+    const int n = p.H * p.W;
+    const long long g = p.list ? (long long)p.list[i] : i;
+    map = g / (2LL * n);
+    e = (int)(g - map * 2LL * n);
+    return edge_ends(e, n, p.H, p.W, u, v);
+}
 struct MstReset : ElemBase {
     using Params = MstRoundParams;
     template <int PH>
     FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
         const long long i = (long long)bx * THREADS + tid;
-        if (i >= p.total) return;
+        if (i >= p.count) return;
         p.best_w[i] = ~0ull;
         p.best_e[i] = ~0u;
+    }
+};
+// later rounds: only the components that still have a cross edge need their minima cleared
+struct MstResetList : ElemBase {
+    using Params = MstRoundParams;
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
+        const long long i = (long long)bx * THREADS + tid;
+        if (i >= p.count) return;
+        long long map; int e, u, v;
+        if (!mst_edge(p, i, map, e, u, v)) return;
+        const long long o = map * p.H * p.W;
+        int ru, rv, t0, t1;
+        pot_find(p.PO + o, u, ru, t0);
+        pot_find(p.PO + o, v, rv, t1);
+        p.best_w[o + ru] = ~0ull; p.best_e[o + ru] = ~0u;
+        p.best_w[o + rv] = ~0ull; p.best_e[o + rv] = ~0u;
     }
 };
 template <int PASS>   // 0: minimum weight per component, 1: minimum edge index among the minimum-weight edges
@@ -163,46 +202,100 @@ struct MstSelect : ElemBase {
     template <int PH>
     FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
         const long long i = (long long)bx * THREADS + tid;
-        if (i >= p.total) return;
-        const int n = p.H * p.W;
-        const long long map = i / (2LL * n);
-        const int e = (int)(i % (2LL * n));
-        int u, v;
-        if (!edge_ends(e, n, p.H, p.W, u, v)) return;
-        const po_t* PO = p.PO + map * n;
+        if (i >= p.count) return;
+        long long map; int e, u, v;
+        if (!mst_edge(p, i, map, e, u, v)) return;
+        const long long o = map * p.H * p.W;
         int ru, rv, t0, t1;
-        pot_find(PO, u, ru, t0);
-        pot_find(PO, v, rv, t1);
+        pot_find(p.PO + o, u, ru, t0);
+        pot_find(p.PO + o, v, rv, t1);
         if (ru == rv) return;
-        const double* rel = p.rel + map * n;
-        const unsigned long long key = f64_bits(rel[u] + rel[v]);
-        unsigned long long* bw = p.best_w + map * n;
+        const unsigned long long key = f64_bits(p.rel[o + u] + p.rel[o + v]);
+        unsigned long long* bw = p.best_w + o;
         if (PASS == 0) {
             atomic_min_u64(bw + ru, key);
             atomic_min_u64(bw + rv, key);
         } else {
-            unsigned* be = p.best_e + map * n;
+            unsigned* be = p.best_e + o;
             if (bw[ru] == key) atomic_min_u32(be + ru, (unsigned)e);
             if (bw[rv] == key) atomic_min_u32(be + rv, (unsigned)e);
         }
     }
 };
-struct MstUnite : ElemBase {
+// block-aggregated append: one global atomic per thread block
+struct AppendState { unsigned value; int keep; unsigned slot; };
+template <class K>
+FCD_HD void block_append(int ph, int tid, unsigned char* smem, AppendState& st, unsigned* list_out, unsigned* counter) {
+    unsigned* sc = reinterpret_cast<unsigned*>(smem);        // [0] block count, [1] block base
+    if (ph == 0) { if (tid == 0) sc[0] = 0; }
+    else if (ph == 1) { if (st.keep) st.slot = atomic_add_u32(sc, 1u); }
+    else if (ph == 2) { if (tid == 0) sc[1] = atomic_add_u32(counter, sc[0]); }
+    else { if (st.keep) list_out[sc[1] + st.slot] = st.value; }
+}
+struct MstListBase : ElemBase {
+    static constexpr int PHASES = 4, SMEM_BYTES = 16;
+    struct State { AppendState a; };
+};
+// edges that some component selected as its minimum (evaluated while PO is not being modified)
+struct MstMark : MstListBase {
     using Params = MstRoundParams;
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem, State& st) {
+        if constexpr (PH == 1) {
+            st.a.keep = 0;
+            const long long i = (long long)bx * THREADS + tid;
+            long long map; int e, u, v;
+            if (i < p.count && mst_edge(p, i, map, e, u, v)) {
+                const long long o = map * p.H * p.W;
+                int ru, rv, t0, t1;
+                pot_find(p.PO + o, u, ru, t0);
+                pot_find(p.PO + o, v, rv, t1);
+                if (ru != rv && (p.best_e[o + ru] == (unsigned)e || p.best_e[o + rv] == (unsigned)e)) {
+                    st.a.keep = 1;
+                    st.a.value = (unsigned)(map * 2LL * p.H * p.W + e);
+                }
+            }
+        }
+        block_append<MstMark>(PH, tid, smem, st.a, p.list_out, p.counters + 2);
+    }
+};
+struct MstUnite : ElemBase {
+    using Params = MstRoundParams;     // list = the chosen edges, count = their number
     template <int PH>
     FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
         const long long i = (long long)bx * THREADS + tid;
-        if (i >= p.total) return;
-        const int n = p.H * p.W;
-        const long long map = i / n;
-        const unsigned e = p.best_e[i];        // only entries of (start-of-round) roots can be set
-        if (e == ~0u) return;
-        int u, v;
-        edge_ends((int)e, n, p.H, p.W, u, v);
-        const float* w = p.w + map * n;
+        if (i >= p.count) return;
+        long long map; int e, u, v;
+        mst_edge(p, i, map, e, u, v);
+        const long long o = map * p.H * p.W;
         // value[u] + 2pi inc[u] continuous with value[v] + 2pi inc[v]:  inc[v] = inc[u] - jump(u, v)
-        const int delta = -jump_between((double)w[u], (double)w[v]);
-        if (pot_unite(p.PO + map * n, u, v, delta)) atomic_add_i32(p.merges, 1);
+        const int delta = -jump_between((double)p.w[o + u], (double)p.w[o + v]);
+        if (pot_unite(p.PO + o, u, v, delta)) atomic_add_u32(p.counters, 1u);
+    }
+};
+// path-compress the end points of this round's edges and keep the edges that still cross components
+struct MstCompact : MstListBase {
+    using Params = MstRoundParams;
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem, State& st) {
+        if constexpr (PH == 1) {
+            st.a.keep = 0;
+            const long long i = (long long)bx * THREADS + tid;
+            long long map; int e, u, v;
+            if (i < p.count && mst_edge(p, i, map, e, u, v)) {
+                const long long o = map * p.H * p.W;
+                int ru, rv, pu, pv;
+                pot_find(p.PO + o, u, ru, pu);
+                pot_find(p.PO + o, v, rv, pv);
+                if (ru != u) p.PO[o + u] = po_pack(ru, pu);      // one 64-bit store: concurrent walks stay consistent
+                if (rv != v) p.PO[o + v] = po_pack(rv, pv);
+                if (ru != rv) {
+                    st.a.keep = 1;
+                    st.a.value = (unsigned)(map * 2LL * p.H * p.W + e);
+                }
+            }
+        }
+        block_append<MstCompact>(PH, tid, smem, st.a, p.list_out, p.counters + 1);
     }
 };
 struct MstFlatten : ElemBase {
@@ -210,7 +303,7 @@ struct MstFlatten : ElemBase {
     template <int PH>
     FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
         const long long i = (long long)bx * THREADS + tid;
-        if (i >= p.total) return;
+        if (i >= p.count) return;
         const int n = p.H * p.W;
         po_t* PO = p.PO + (i / n) * n;
         const int px = (int)(i % n);
@@ -224,7 +317,7 @@ struct MstApply : ElemBase {
     template <int PH>
     FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
         const long long i = (long long)bx * THREADS + tid;
-        if (i >= p.total) return;
+        if (i >= p.count) return;
         const int n = p.H * p.W;
         const po_t* PO = p.PO + (i / n) * n;
         int root, pot;
