@@ -491,25 +491,30 @@ struct PlanImpl {
         }
         const size_t cap = (size_t)kUnwrapMaps * n;
         u_rel.alloc(cap); u_po.alloc(cap); u_bw.alloc(cap); u_be.alloc(cap); u_counters.alloc(4);
-        u_list[0].alloc(2 * cap); u_list[1].alloc(2 * cap); u_chosen.alloc(cap);
+        u_list[0].alloc(2 * cap); u_list[1].alloc(2 * cap); u_chosen.alloc(cap + 1024);
         for (int m0 = 0; m0 < n_maps; m0 += kUnwrapMaps) {
             const int nm = std::min(kUnwrapMaps, n_maps - m0);
             const long long total = nm * n;
             const float* w = wrapped + m0 * n;
             launch<MstReliability>(blocks_for(total), 1, s, MstRelParams{w, u_border.ptr, u_rel.ptr, u_po.ptr, total, H, W});
             MstRoundParams base{w, u_rel.ptr, u_po.ptr, u_bw.ptr, u_be.ptr, nullptr, nullptr, u_counters.ptr, total, H, W, nullptr};
-            launch<MstReset>(blocks_for(total), 1, s, base);
             const unsigned* list = nullptr;            // round 0: all 2n edges of every map, enumerated implicitly
             long long count = 2 * total;
             for (int round = 0; round < 64 && count > 0; ++round) {
                 rt::dmemset(u_counters.ptr, 0, 4 * sizeof(unsigned), s);
                 MstRoundParams rp = base;
                 rp.list = list; rp.count = count;
-                if (round > 0) launch<MstResetList>(blocks_for(count), 1, s, rp);
-                launch<MstSelect<0>>(blocks_for(count), 1, s, rp);
-                launch<MstSelect<1>>(blocks_for(count), 1, s, rp);
                 rp.list_out = u_chosen.ptr;
-                launch<MstMark>(blocks_for(count), 1, s, rp);
+                if (round == 0) {                       // every pixel is a component: its best edge is a local minimum
+                    MstRoundParams r0 = base;
+                    r0.list_out = u_chosen.ptr;
+                    launch<MstRound0>(blocks_for(total), 1, s, r0);
+                } else {
+                    launch<MstResetList>(blocks_for(count), 1, s, rp);
+                    launch<MstSelect<0>>(blocks_for(count), 1, s, rp);
+                    launch<MstSelect<1>>(blocks_for(count), 1, s, rp);
+                    launch<MstMark>(blocks_for(count), 1, s, rp);
+                }
                 unsigned c[4];
                 rt::d2h(c, u_counters.ptr, sizeof(c), s);
                 const long long chosen = c[2];

@@ -72,12 +72,41 @@ FCD_HD void pot_find(const po_t* PO, int x, int& root, int& pot) {
         x = par;
     }
 }
+// The same walk with path halving: a non-root node is re-pointed at its grandparent with the summed offset.
+// Links are never removed and pot(x) - pot(ancestor) never changes, so any (ancestor, offset) pair read at
+// any time stays valid: concurrent 64-bit stores of such pairs are benign.  Keeps the chains that the
+// unions of one round build under each other short.
+FCD_HD void po_store(po_t* p, po_t v) {
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<volatile po_t*>(p) = v;
+#else
+    *p = v;
+#endif
+}
+FCD_HD void pot_find_halving(po_t* PO, int x, int& root, int& pot) {
+    int acc = 0;
+    for (;;) {
+        const po_t v = po_load(PO + x);
+        const int par = po_parent(v);
+        if (par == x) { root = x; pot = acc; return; }
+        const po_t g = po_load(PO + par);
+        const int gp = po_parent(g);
+        if (gp != par) {
+            po_store(PO + x, po_pack(gp, po_off(v) + po_off(g)));
+            acc += po_off(v) + po_off(g);
+            x = gp;
+        } else {
+            acc += po_off(v);
+            x = par;
+        }
+    }
+}
 // make pot(v) = pot(u) + delta by linking the two roots (larger index under smaller)
 FCD_HD bool pot_unite(po_t* PO, int u, int v, int delta) {
     for (;;) {
         int ru, pu, rv, pv;
-        pot_find(PO, u, ru, pu);
-        pot_find(PO, v, rv, pv);
+        pot_find_halving(PO, u, ru, pu);
+        pot_find_halving(PO, v, rv, pv);
         if (ru == rv) return false;
         int child, parent, off;
         if (ru < rv) { child = rv; parent = ru; off = pu + delta - pv; }
@@ -235,6 +264,44 @@ FCD_HD void block_append(int ph, int tid, unsigned char* smem, AppendState& st, 
 struct MstListBase : ElemBase {
     static constexpr int PHASES = 4, SMEM_BYTES = 16;
     struct State { AppendState a; };
+};
+// Round 0: every pixel is its own component, so its minimum outgoing edge is the minimum over its (at most four)
+// incident edges under the same (weight, edge index) order -- no atomics, one pass over the pixels.  The chosen
+// edges go straight to the list MstUnite consumes (an edge picked from both ends appears twice; the second
+// union is a no-op).
+struct MstRound0 : MstListBase {
+    using Params = MstRoundParams;     // count = maps * n pixels
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem, State& st) {
+        if constexpr (PH == 1) {
+            st.a.keep = 0;
+            const long long i = (long long)bx * THREADS + tid;
+            if (i < p.count) {
+                const int n = p.H * p.W;
+                const long long map = i / n;
+                const int px = (int)(i - map * n);
+                const int r = px / p.W, c = px - r * p.W;
+                const double* rel = p.rel + map * n;
+                const double r0 = rel[px];
+                unsigned long long bw = ~0ull;
+                unsigned be = ~0u;
+                auto consider = [&](bool ok, int q, unsigned e) {
+                    if (!ok) return;
+                    const unsigned long long key = f64_bits(r0 + rel[q]);     // the sum is commutative: same key from both ends
+                    if (key < bw || (key == bw && e < be)) { bw = key; be = e; }
+                };
+                consider(c > 0, px - 1, (unsigned)(px - 1));                  // horizontal edge (px-1, px) has index px-1
+                consider(c + 1 < p.W, px + 1, (unsigned)px);
+                consider(r > 0, px - p.W, (unsigned)(n + px - p.W));          // vertical edge (px-W, px) has index n + px-W
+                consider(r + 1 < p.H, px + p.W, (unsigned)(n + px));
+                if (be != ~0u) {
+                    st.a.keep = 1;
+                    st.a.value = (unsigned)(map * 2LL * n + be);
+                }
+            }
+        }
+        block_append<MstRound0>(PH, tid, smem, st.a, p.list_out, p.counters + 2);
+    }
 };
 // edges that some component selected as its minimum (evaluated while PO is not being modified)
 struct MstMark : MstListBase {
