@@ -505,30 +505,27 @@ struct PlanImpl {
                 MstRoundParams rp = base;
                 rp.list = list; rp.count = count;
                 rp.list_out = u_chosen.ptr;
-                if (round == 0) {                       // every pixel is a component: its best edge is a local minimum
-                    MstRoundParams r0 = base;
-                    r0.list_out = u_chosen.ptr;
-                    launch<MstRound0>(blocks_for(total), 1, s, r0);
+                if (round == 0) {                       // every pixel is a component: local minima, no unions needed
+                    launch<MstRound0>(blocks_for(total), 1, s, base);
+                    launch<MstFlatten>(blocks_for(total), 1, s, base);
                 } else {
                     launch<MstResetList>(blocks_for(count), 1, s, rp);
                     launch<MstSelect<0>>(blocks_for(count), 1, s, rp);
                     launch<MstSelect<1>>(blocks_for(count), 1, s, rp);
                     launch<MstMark>(blocks_for(count), 1, s, rp);
-                }
-                unsigned c[4];
-                rt::d2h(c, u_counters.ptr, sizeof(c), s);
-                const long long chosen = c[2];
-                if (chosen == 0) break;                 // no component has an outgoing edge left
-                MstRoundParams up = base;
-                up.list = u_chosen.ptr; up.count = chosen;
-                launch<MstUnite>(blocks_for(chosen), 1, s, up);
-                if (round < 2) {                        // early rounds touch most pixels: flatten everything
-                    MstRoundParams fp = base;
-                    launch<MstFlatten>(blocks_for(total), 1, s, fp);
+                    unsigned c[4];
+                    rt::d2h(c, u_counters.ptr, sizeof(c), s);
+                    const long long chosen = c[2];
+                    if (chosen == 0) break;             // no component has an outgoing edge left
+                    MstRoundParams up = base;
+                    up.list = u_chosen.ptr; up.count = chosen;
+                    launch<MstUnite>(blocks_for(chosen), 1, s, up);
+                    if (round < 2) launch<MstFlatten>(blocks_for(total), 1, s, base);   // still touches most pixels
                 }
                 unsigned* out_list = u_list[round & 1].ptr;
                 rp.list_out = out_list;
                 launch<MstCompact>(blocks_for(count), 1, s, rp);
+                unsigned c[4];
                 rt::d2h(c, u_counters.ptr, sizeof(c), s);
                 ++unwrap_rounds;
                 list = out_list;

@@ -266,41 +266,46 @@ struct MstListBase : ElemBase {
     struct State { AppendState a; };
 };
 // Round 0: every pixel is its own component, so its minimum outgoing edge is the minimum over its (at most four)
-// incident edges under the same (weight, edge index) order -- no atomics, one pass over the pixels.  The chosen
-// edges go straight to the list MstUnite consumes (an edge picked from both ends appears twice; the second
-// union is a no-op).
-struct MstRound0 : MstListBase {
+// incident edges under the same (weight, edge index) order.  The picks form a forest once every mutual pick
+// (the only possible cycle under a strict order) is rooted at its smaller pixel, so each pixel simply writes
+// its own union-find word -- (picked neighbour, integer offset across the edge) -- with no atomics and no
+// union at all; MstFlatten then points everything at the roots.
+struct MstRound0 : ElemBase {
     using Params = MstRoundParams;     // count = maps * n pixels
+    // best incident edge of pixel px: edge index and the pixel at its other end
+    FCD_HD static void best_edge(const double* rel, int px, int H, int W, unsigned& be, int& other) {
+        const int n = H * W;
+        const int r = px / W, c = px - r * W;
+        const double r0 = rel[px];
+        unsigned long long bw = ~0ull;
+        be = ~0u; other = -1;
+        auto consider = [&](bool ok, int q, unsigned e) {
+            if (!ok) return;
+            const unsigned long long key = f64_bits(r0 + rel[q]);     // the sum is commutative: same key from both ends
+            if (key < bw || (key == bw && e < be)) { bw = key; be = e; other = q; }
+        };
+        consider(c > 0, px - 1, (unsigned)(px - 1));                  // horizontal edge (px-1, px) has index px-1
+        consider(c + 1 < W, px + 1, (unsigned)px);
+        consider(r > 0, px - W, (unsigned)(n + px - W));              // vertical edge (px-W, px) has index n + px-W
+        consider(r + 1 < H, px + W, (unsigned)(n + px));
+    }
     template <int PH>
-    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem, State& st) {
-        if constexpr (PH == 1) {
-            st.a.keep = 0;
-            const long long i = (long long)bx * THREADS + tid;
-            if (i < p.count) {
-                const int n = p.H * p.W;
-                const long long map = i / n;
-                const int px = (int)(i - map * n);
-                const int r = px / p.W, c = px - r * p.W;
-                const double* rel = p.rel + map * n;
-                const double r0 = rel[px];
-                unsigned long long bw = ~0ull;
-                unsigned be = ~0u;
-                auto consider = [&](bool ok, int q, unsigned e) {
-                    if (!ok) return;
-                    const unsigned long long key = f64_bits(r0 + rel[q]);     // the sum is commutative: same key from both ends
-                    if (key < bw || (key == bw && e < be)) { bw = key; be = e; }
-                };
-                consider(c > 0, px - 1, (unsigned)(px - 1));                  // horizontal edge (px-1, px) has index px-1
-                consider(c + 1 < p.W, px + 1, (unsigned)px);
-                consider(r > 0, px - p.W, (unsigned)(n + px - p.W));          // vertical edge (px-W, px) has index n + px-W
-                consider(r + 1 < p.H, px + p.W, (unsigned)(n + px));
-                if (be != ~0u) {
-                    st.a.keep = 1;
-                    st.a.value = (unsigned)(map * 2LL * n + be);
-                }
-            }
-        }
-        block_append<MstRound0>(PH, tid, smem, st.a, p.list_out, p.counters + 2);
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
+        const long long i = (long long)bx * THREADS + tid;
+        if (i >= p.count) return;
+        const int n = p.H * p.W;
+        const long long o = (i / n) * n;
+        const int px = (int)(i - o);
+        const double* rel = p.rel + o;
+        unsigned be, bq; int q, qq;
+        best_edge(rel, px, p.H, p.W, be, q);
+        if (q < 0) return;                                            // a 1 x 1 map: stays its own root
+        best_edge(rel, q, p.H, p.W, bq, qq);
+        if (bq == be && px < q) return;                               // mutual pick: the smaller pixel is the root
+        // pot(v) = pot(u) - jump(u, v) for the edge (u, v), u < v   (same convention as MstUnite)
+        const float* w = p.w + o;
+        const int off = q < px ? -jump_between((double)w[q], (double)w[px]) : jump_between((double)w[px], (double)w[q]);
+        p.PO[o + px] = po_pack(q, off);
     }
 };
 // edges that some component selected as its minimum (evaluated while PO is not being modified)
@@ -387,9 +392,10 @@ struct MstApply : ElemBase {
         if (i >= p.count) return;
         const int n = p.H * p.W;
         const po_t* PO = p.PO + (i / n) * n;
-        int root, pot;
+        int root, pot, root0, pot0;
         pot_find(PO, (int)(i % n), root, pot);
-        p.out[i] = (float)((double)p.w[i] + 2.0 * kPiD * (double)pot);
+        pot_find(PO, 0, root0, pot0);                   // normalisation: pixel (0, 0) keeps its wrapped value
+        p.out[i] = (float)((double)p.w[i] + 2.0 * kPiD * (double)(pot - pot0));
     }
 };
 
