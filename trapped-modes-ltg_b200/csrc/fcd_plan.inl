@@ -509,7 +509,6 @@ struct PlanImpl {
                     launch<MstRound0>(blocks_for(total), 1, s, base);
                     launch<MstFlatten>(blocks_for(total), 1, s, base);
                 } else {
-                    launch<MstResetList>(blocks_for(count), 1, s, rp);
                     launch<MstSelect<0>>(blocks_for(count), 1, s, rp);
                     launch<MstSelect<1>>(blocks_for(count), 1, s, rp);
                     launch<MstMark>(blocks_for(count), 1, s, rp);

@@ -208,23 +208,6 @@ struct MstReset : ElemBase {
         p.best_e[i] = ~0u;
     }
 };
-// later rounds: only the components that still have a cross edge need their minima cleared
-struct MstResetList : ElemBase {
-    using Params = MstRoundParams;
-    template <int PH>
-    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
-        const long long i = (long long)bx * THREADS + tid;
-        if (i >= p.count) return;
-        long long map; int e, u, v;
-        if (!mst_edge(p, i, map, e, u, v)) return;
-        const long long o = map * p.H * p.W;
-        int ru, rv, t0, t1;
-        pot_find(p.PO + o, u, ru, t0);
-        pot_find(p.PO + o, v, rv, t1);
-        p.best_w[o + ru] = ~0ull; p.best_e[o + ru] = ~0u;
-        p.best_w[o + rv] = ~0ull; p.best_e[o + rv] = ~0u;
-    }
-};
 template <int PASS>   // 0: minimum weight per component, 1: minimum edge index among the minimum-weight edges
 struct MstSelect : ElemBase {
     using Params = MstRoundParams;
@@ -364,6 +347,10 @@ struct MstCompact : MstListBase {
                 if (ru != rv) {
                     st.a.keep = 1;
                     st.a.value = (unsigned)(map * 2LL * p.H * p.W + e);
+                    // the two components take part in the next round: clear their minima here (same value
+                    // from every thread that touches them)
+                    p.best_w[o + ru] = ~0ull; p.best_e[o + ru] = ~0u;
+                    p.best_w[o + rv] = ~0ull; p.best_e[o + rv] = ~0u;
                 }
             }
         }
