@@ -612,7 +612,6 @@ struct PlanImpl {
         t_valid.alloc((size_t)nblk);
         rt::dmemset(t_mean.ptr, 0, sizeof(double) * (size_t)nblk * npos, s);
         rt::dmemset(t_valid.ptr, 0, sizeof(int) * (size_t)nblk, s);
-        const long long total = (long long)rows * cols;
         const long long segs = (long long)bs * brows * bcols;
         launch<BlockValidCount>(blocks_for(segs), 1, s, BlockValidParams{first, t_valid.ptr, rows, cols, bs, brows, bcols, segs});
         TemporalSpecParams p{maps, first, t_tw.ptr, t_chirp.ptr, t_bspec.ptr, t_mean.ptr, zero, n_frames, npos, rows, cols, bs, brows, bcols};
