@@ -73,7 +73,7 @@ def measured_peak_gbs():
 def make_frames_gpu(n, count, seed, device, chunk=8, peak_range=(0.2, 0.8)):
     import torch
 
-    from oracle import fcd_oracle as o  # generator parameters only (host scalars)
+    from fcd_b200 import synthetic as o  # input generation only (no oracle on the product arm)
     rng = np.random.default_rng(seed)
     a, b, eps = 60.0 * n / 1024.0, 3.0 * n / 1024.0, 0.1
     ref = torch.from_numpy(o.rotated_board(n)).to(device)
@@ -266,8 +266,8 @@ def run_ours(args):
         args.frames_per_launch = 128 if n <= 2048 else 32
     plan = HeightMapPlan((n, n), args.frames_per_launch, dev)
     ref, frames = make_frames_gpu(n, F, SEED + rank, dev, peak_range=tuple(args.peak_px))
-    from oracle import fcd_oracle as o
-    sq = o.board_square_size(n)
+    from fcd_b200 import synthetic
+    sq = synthetic.board_square_size(n)
     cal = plan.bind(ref, square_size=sq, height=1.0)
     out = torch.empty_like(frames)
     torch.cuda.synchronize()

@@ -333,56 +333,19 @@ def compute_height_map(reference, displaced, square_size, layers=None, height=No
 
 
 # --------------------------------------------------------------------------------------
-# synthetic inputs  (generator template: pyval/val.py:79-108)
+# synthetic inputs  (SURVEY.md section 8(d)): shared with bench.py, which may not import oracle/ on its
+# product arm -- the generators live in the package's input-generation module
 # --------------------------------------------------------------------------------------
-def rotated_board(n: int, a: float | None = None, b: float | None = None, eps: float = 0.1,
-                  uy=None, ux=None, dtype=np.float32) -> np.ndarray:
-    """Exactly periodic rotated checkerboard I0(r - u).  With uy=ux=None returns I0.
-    A = 2pi(a*y + b*x)/n, B = 2pi(-b*y + a*x)/n,
-    I0 = 0.5 + 0.25*((1+eps)cos(A-B) - cos(A+B))/(1+eps/2)."""
-    a = 60.0 * n / 1024.0 if a is None else a
-    b = 3.0 * n / 1024.0 if b is None else b
-    y = np.arange(n, dtype=np.float64)[:, None]
-    x = np.arange(n, dtype=np.float64)[None, :]
-    if uy is not None:
-        y = y - uy
-        x = x - ux
-    A = TWO_PI * (a * y + b * x) / n
-    B = TWO_PI * (-b * y + a * x) / n
-    img = 0.5 + 0.25 * ((1.0 + eps) * np.cos(A - B) - np.cos(A + B)) / (1.0 + eps / 2.0)
-    return img.astype(dtype)
+import importlib.util as _ilu
+import os as _os
 
-
-def board_square_size(n: int, a: float | None = None) -> float:
-    a = 60.0 * n / 1024.0 if a is None else a
-    return n / (2.0 * a)
-
-
-def gaussian_bump_displacement(n: int, center, sigma: float, peak_disp: float, H: float = 1.0):
-    """h = A*exp(-r^2/2sigma^2); u = -H*grad(h), scaled so max|u| = peak_disp pixels.
-    Returns (h, u_row, u_col)."""
-    y = np.arange(n, dtype=np.float64)[:, None] - center[0]
-    x = np.arange(n, dtype=np.float64)[None, :] - center[1]
-    g = np.exp(-(y * y + x * x) / (2.0 * sigma * sigma))
-    # |grad g| peaks at r = sigma with value exp(-1/2)/sigma
-    amp = peak_disp * sigma * np.exp(0.5) / H
-    h = amp * g
-    hy = -amp * y / (sigma * sigma) * g
-    hx = -amp * x / (sigma * sigma) * g
-    return h, -H * hy, -H * hx
-
-
-def synthetic_frames(n: int, count: int, seed: int = 20251018, peak_range=(0.2, 0.8), dtype=np.float32):
-    """Reference + ``count`` deformed frames + ground-truth heights."""
-    rng = np.random.default_rng(seed)
-    ref = rotated_board(n, dtype=dtype)
-    frames = np.empty((count, n, n), dtype=dtype)
-    truth = np.empty((count, n, n), dtype=np.float64)
-    for i in range(count):
-        cy, cx = rng.uniform(0.35 * n, 0.65 * n, size=2)
-        sigma = rng.uniform(n / 12.0, n / 6.0)
-        peak = rng.uniform(*peak_range)
-        h, uy, ux = gaussian_bump_displacement(n, (cy, cx), sigma, peak)
-        frames[i] = rotated_board(n, uy=uy, ux=ux, dtype=dtype)
-        truth[i] = h
-    return ref, frames, truth
+_spec = _ilu.spec_from_file_location(
+    "fcd_b200_synthetic",
+    _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "trapped-modes-ltg_b200", "fcd_b200",
+                  "synthetic.py"))
+_synthetic = _ilu.module_from_spec(_spec)
+_spec.loader.exec_module(_synthetic)
+rotated_board = _synthetic.rotated_board
+board_square_size = _synthetic.board_square_size
+gaussian_bump_displacement = _synthetic.gaussian_bump_displacement
+synthetic_frames = _synthetic.synthetic_frames

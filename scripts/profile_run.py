@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "trapped-modes-l
 import torch
 from bench import make_frames_gpu, SEED
 from fcd_b200 import HeightMapPlan
-from oracle import fcd_oracle as o
+from fcd_b200 import synthetic as o
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 fpl = int(sys.argv[2]) if len(sys.argv) > 2 else 4

@@ -18,7 +18,7 @@ import torch.distributed as dist
 import fcd_b200
 from fcd_b200.engine import shard_range, gather_height_maps
 from bench import make_frames_gpu, SEED
-from oracle import fcd_oracle as o
+from fcd_b200 import synthetic as o
 
 total = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 chunk = int(sys.argv[2]) if len(sys.argv) > 2 else 128

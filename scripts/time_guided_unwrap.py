@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "trapped-modes-l
 import torch
 import fcd_b200
 from bench import make_frames_gpu, SEED
-from oracle import fcd_oracle as o
+from fcd_b200 import synthetic as o
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 dev = torch.device("cuda", 0)

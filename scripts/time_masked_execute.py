@@ -3,7 +3,7 @@ sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/trapped-modes-l
 import numpy as np, torch
 from fcd_b200 import HeightMapPlan
 from bench import make_frames_gpu, SEED
-from oracle import fcd_oracle as o
+from fcd_b200 import synthetic as o
 n=2048; dev=torch.device("cuda",0)
 for F in (32, 64):
     plan=HeightMapPlan((n,n),F,dev)
