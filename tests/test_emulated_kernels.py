@@ -236,3 +236,23 @@ def test_thread_order_independence(golden):
     for order in (1, 2):
         for a, b in zip(base, run(order)):
             assert np.array_equal(a, b)
+
+
+def test_empty_batches_and_bad_modes():
+    """Edge cases of the C ABI: empty batches are no-ops, an unknown unwrap mode is an argument error."""
+    from fcd_b200 import synthetic as syn
+    plan = EmulPlan((64, 64), 2)
+    ref = syn.rotated_board(64, a=6.0, b=1.0).astype(np.float64)
+    bind_like_reference(plan, ref, syn.board_square_size(64, 6.0))
+    assert plan.execute(np.zeros((0, 64, 64), np.float32)).shape == (0, 64, 64)
+    assert plan.unwrap_phase(np.zeros((0, 64, 64), np.float32)).shape == (0, 64, 64)
+    assert plan.structure_mask(np.zeros((0, 64, 64), np.float32)).shape == (0, 64, 64)
+    assert plan.mask_center(np.zeros((0, 64, 64), np.uint8)) == []
+    with pytest.raises(_native.FcdError) as e:
+        plan.execute(np.zeros((1, 64, 64), np.float32), unwrap=3)
+    assert e.value.code == _native.FCD_ERR_INVALID
+    # the reference frame itself demodulates to a flat surface (zero phases), with every unwrap mode
+    for mode in (0, 1, 2):
+        h = plan.execute(ref.astype(np.float32), unwrap=mode)
+        assert np.abs(h).max() < 1e-4
+    plan.close()
