@@ -113,8 +113,8 @@ int fcd_unwrap_phase(fcd_plan* plan, const float* wrapped_dev, int n_maps, float
  *   non-negative frequencies (analyze.py:603-614), pixels that are zero in first_map_dev excluded
  *   (analyze.py:568,590) and `zero` subtracted (analyze.py:585).  mean_out: host,
  *   [blocks][npos] float64 with npos = n/2 (n even) or (n+1)/2; valid_out: host, [blocks] valid-pixel
- *   counts (0 -> NaN row).  n must satisfy fcd_temporal_frames_supported (a power of two in
- *   [64, 4096], or at most 2048 through a chirp convolution).
+ *   counts (0 -> NaN row).  n must satisfy fcd_temporal_frames_supported: a power of two in [64, 4096] or at
+ *   most 2048 (one chirp convolution), or a product of two factors <= 2048 (two levels; e.g. 20,000 = 160 x 125).
  * fcd_temporal_accumulate: adds frames [t0, t0 + n_chunk) of an n_total-frame series to the
  *   DFT sums of n_bins bins per block (bins: host, [blocks][n_bins]); acc_dev is
  *   [n_bins][2][rows*cols] float64 (init != 0 overwrites).  Any n_total; additive over chunks
@@ -126,6 +126,12 @@ int fcd_temporal_mean_spectrum(fcd_plan* plan, const float* maps_dev, int n_fram
                                const float* first_map_dev, float zero, int block_size, int block_rows, int block_cols,
                                double* mean_out, int* valid_out, void* stream);
 int fcd_temporal_frames_supported(int n_frames);
+/* The same with the two-level factorisation n = n1 * (n / n1) forced (long series take this path on their own:
+ * X[k1 + n1 k2] from length-n1 transforms over the frames n1' * n2 + n2', a twiddle, and length-n2 transforms,
+ * through an [n][pixels] complex workspace per chunk of spatial blocks); for tests of that path on short series. */
+int fcd_temporal_mean_spectrum_split(fcd_plan* plan, const float* maps_dev, int n_frames, int rows, int cols,
+                                     const float* first_map_dev, float zero, int block_size, int block_rows, int block_cols,
+                                     int n1, double* mean_out, int* valid_out, void* stream);
 int fcd_temporal_accumulate(fcd_plan* plan, const float* maps_dev, int n_chunk, int t0, int n_total, int rows, int cols,
                             float zero, int block_size, int block_rows, int block_cols, const int* bins, int n_bins,
                             double* acc_dev, int init, void* stream);

@@ -112,16 +112,20 @@ class EmulPlan:
         _native.check(self.lib, self.lib.fcd_unwrap_phase(self.h, _p(w), n, _p(out), None))
         return out
 
-    def temporal_mean_spectrum(self, maps, first, zero, bpr):
+    def temporal_mean_spectrum(self, maps, first, zero, bpr, n1=0):
         maps = np.ascontiguousarray(maps, dtype=np.float32)
         n, rows, cols = maps.shape
         first = None if first is None else np.ascontiguousarray(first, dtype=np.float32)
         npos = n // 2 if n % 2 == 0 else (n + 1) // 2
         mean = np.zeros((bpr * bpr, npos), np.float64)
         valid = np.zeros(bpr * bpr, np.int32)
-        _native.check(self.lib, self.lib.fcd_temporal_mean_spectrum(
-            self.h, _p(maps), n, rows, cols, _p(first), float(zero), rows // bpr, bpr, bpr,
-            mean.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), valid.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), None))
+        mp_, vp_ = mean.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), valid.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+        if n1:
+            _native.check(self.lib, self.lib.fcd_temporal_mean_spectrum_split(
+                self.h, _p(maps), n, rows, cols, _p(first), float(zero), rows // bpr, bpr, bpr, int(n1), mp_, vp_, None))
+        else:
+            _native.check(self.lib, self.lib.fcd_temporal_mean_spectrum(
+                self.h, _p(maps), n, rows, cols, _p(first), float(zero), rows // bpr, bpr, bpr, mp_, vp_, None))
         return mean, valid
 
     def temporal_harmonics(self, maps, bins, n_total=None, t0=0, zero=0.0, bpr=2, first=None, chunks=(None,)):

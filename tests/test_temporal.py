@@ -86,11 +86,28 @@ def test_emulated_kernels_match_golden(gt, ci):
     plan.close()
 
 
+@pytest.mark.parametrize("n,n1", [(48, 8), (35, 7), (90, 10)])
+def test_emulated_two_level_transform(n, n1):
+    """Long series take N = N1 * N2 in two levels of chirp-convolution transforms; forced here on short ones."""
+    from tests.emul_lib import EmulPlan
+    maps = to.synthetic_maps(n, (64, 64), 4, seed=3)
+    plan = EmulPlan((64, 64))
+    mean, valid = plan.temporal_mean_spectrum(maps, maps[0], 0.01, 2, n1=n1)
+    direct, _ = plan.temporal_mean_spectrum(maps, maps[0], 0.01, 2)
+    for b in range(4):
+        ref = to.mean_spectrum(maps, 4, b, 0.01)
+        assert np.abs(mean[b] - ref).max() <= 1e-6 * ref.max()
+        assert np.abs(mean[b] - direct[b]).max() <= 1e-6 * ref.max()
+    plan.close()
+
+
 def test_unsupported_series_length_is_an_error():
     from fcd_b200 import _native
     from tests.emul_lib import EmulPlan, lib
     assert lib().fcd_temporal_frames_supported(4096) and lib().fcd_temporal_frames_supported(2048)
-    assert lib().fcd_temporal_frames_supported(1000) and not lib().fcd_temporal_frames_supported(3000)
+    assert lib().fcd_temporal_frames_supported(1000) and lib().fcd_temporal_frames_supported(3000)
+    assert lib().fcd_temporal_frames_supported(20000)                   # 160 x 125
+    assert not lib().fcd_temporal_frames_supported(2 * 2053)            # 2 x a prime above 2048
     plan = EmulPlan((64, 64))
     with pytest.raises(_native.FcdError):
         plan.temporal_harmonics(np.zeros((4, 64, 64), np.float32), np.zeros((4, 9), np.int32))    # > 8 bins
@@ -181,6 +198,14 @@ def test_gpu_full_size_series_properties():
         a = res.amps[i * bs:(i + 1) * bs, j * bs:(j + 1) * bs]
         assert abs(float(a[..., 0].mean()) - 0.5) < 1e-3          # first entry: the DC bin (0 * f0)
         assert abs(float(a[..., 1].mean()) - (1 + 0.01 * b)) < 1e-3
+    # a long series: 2500 = 50 x 50 frames takes the two-level path on its own
+    tt = torch.arange(2500, device="cuda", dtype=torch.float32)
+    long = (torch.cos(2 * np.pi * 137 * tt / 2500)[:, None, None] * (1 + torch.rand((1, 64, 64), device="cuda"))
+            + 0.05 * torch.randn((2500, 64, 64), device="cuda"))
+    res_long = tp.block_amplitudes(long, tasa=500, mode=2, num_blocks=4)
+    assert all(abs(f - 137 * 500 / 2500) < 1e-9 for f in res_long.f0)
+    ref = to.mean_spectrum(long.cpu().numpy(), 4, 2)
+    assert np.abs(res_long.mean_spectrum[2] - ref).max() <= 5e-6 * ref.max()
     m1000 = maps[:, :64, :64].repeat(2, 1, 1)[:1000].contiguous()
     mean, _ = tp.mean_spectra(m1000, m1000[0].clone(), 0.0, 32, 2, 2, tp.get_plan((64, 64), 1))
     ref = to.mean_spectrum(m1000.cpu().numpy(), 4, 3)

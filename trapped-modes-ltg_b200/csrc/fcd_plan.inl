@@ -541,11 +541,14 @@ struct PlanImpl {
     // analyze.block_amplitude (pydata/analyze.py:542-641): see fcd_temporal.cuh
     template <int L> struct TuneT { static constexpr int G = L >= 4096 ? 2 : (L >= 2048 ? 4 : 8); };
     int t_len = 0, t_n = 0;                 // cached tables: transform length, number of frames
-    rt::DevBuf<cf> t_tw, t_chirp, t_bspec;
+    rt::DevBuf<cf> t_tw, t_twn, t_ws;
+    const cf* t_chirp_ptr = nullptr;
+    const cf* t_bspec_ptr = nullptr;
+    int t_twn_n = 0;
     rt::DevBuf<double> t_mean, t_twd;
     rt::DevBuf<int> t_valid;
 
-    static int temporal_length(int n_frames) {        // 0: not supported
+    static int temporal_length(int n_frames) {        // single-level transform length; 0: needs the two-level path
         if (n_frames >= 64 && n_frames <= 4096 && (n_frames & (n_frames - 1)) == 0) return n_frames;
         int l = 64;
         while (l < 2 * n_frames - 1) l *= 2;
@@ -571,29 +574,57 @@ struct PlanImpl {
             }
         }
     }
+    // engine twiddles + Bluestein tables of one transform length
+    struct BlueTables {
+        int n = 0, len = 0;
+        rt::DevBuf<cf> tw, chirp, bspec;
+    };
+    static int bluestein_length(int n) {                 // power of two >= 2n - 1 (>= 64); 0: longer than the engine
+        int l = 64;
+        while (l < 2 * n - 1) l *= 2;
+        return l <= 4096 ? l : 0;
+    }
+    BlueTables t_single, t_lvl[2];
+    void build_blue(BlueTables& t, int n, int len, rt::stream_t s) {
+        if (t.n == n && t.len == len) return;
+        FCD_DISPATCH_L(len, { t.tw.upload(Fft<L, -1, float>::make_table(), s); })
+        // Bluestein: X[k] = conj(c[k]) * sum_t (x[t] conj(c[t])) c[k - t],  c[m] = exp(i pi m^2 / N)
+        std::vector<std::complex<double>> c((size_t)n), b((size_t)len, 0.0);
+        for (int m = 0; m < n; ++m) {
+            const long long q = ((long long)m * m) % (2LL * n);
+            const double ang = M_PI * (double)q / (double)n;
+            c[m] = {std::cos(ang), std::sin(ang)};
+            b[m] = c[m];
+            if (m) b[len - m] = c[m];
+        }
+        host_fft(b);
+        std::vector<cf> hc((size_t)n), hb((size_t)len);
+        for (int m = 0; m < n; ++m) hc[m] = mk<float>((float)c[m].real(), (float)c[m].imag());
+        for (int m = 0; m < len; ++m) hb[m] = mk<float>((float)(b[m].real() / len), (float)(b[m].imag() / len));
+        t.chirp.upload(hc, s);
+        t.bspec.upload(hb, s);
+        t.n = n; t.len = len;
+    }
     void temporal_tables(int n_frames, rt::stream_t s) {
         const int len = temporal_length(n_frames);
-        if (!len) rt::fail("temporal spectrum: the number of frames must be a power of two in [64, 4096] or at most 2048");
+        if (!len) rt::fail("temporal spectrum: unsupported single-level length");
         if (len == t_len && n_frames == t_n) return;
         FCD_DISPATCH_L(len, { t_tw.upload(Fft<L, -1, float>::make_table(), s); })
         if (len != n_frames) {
-            // Bluestein: X[k] = conj(c[k]) * sum_t (x[t] conj(c[t])) c[k - t],  c[m] = exp(i pi m^2 / N)
-            std::vector<std::complex<double>> c((size_t)n_frames), b((size_t)len, 0.0);
-            for (int m = 0; m < n_frames; ++m) {
-                const long long q = ((long long)m * m) % (2LL * n_frames);
-                const double ang = M_PI * (double)q / (double)n_frames;
-                c[m] = {std::cos(ang), std::sin(ang)};
-                b[m] = c[m];
-                if (m) b[len - m] = c[m];
-            }
-            host_fft(b);
-            std::vector<cf> hc((size_t)n_frames), hb((size_t)len);
-            for (int m = 0; m < n_frames; ++m) hc[m] = mk<float>((float)c[m].real(), (float)c[m].imag());
-            for (int m = 0; m < len; ++m) hb[m] = mk<float>((float)(b[m].real() / len), (float)(b[m].imag() / len));
-            t_chirp.upload(hc, s);
-            t_bspec.upload(hb, s);
+            build_blue(t_single, n_frames, len, s);
+            t_chirp_ptr = t_single.chirp.ptr; t_bspec_ptr = t_single.bspec.ptr;
         }
         t_len = len; t_n = n_frames;
+    }
+    // N = N1 * N2 with both factors within reach of one chirp convolution (N1 >= N2, as balanced as possible)
+    static bool temporal_split(int n_frames, int& n1, int& n2) {
+        for (int d = (int)std::sqrt((double)n_frames); d >= 2; --d)
+            if (n_frames % d == 0 && n_frames / d <= 2048) { n1 = n_frames / d; n2 = d; return true; }
+        return false;
+    }
+    static bool temporal_supported(int n_frames) {
+        int a, b;
+        return n_frames >= 2 && (temporal_length(n_frames) != 0 || temporal_split(n_frames, a, b));
     }
     static int temporal_npos(int n_frames) { return n_frames % 2 == 0 ? n_frames / 2 : (n_frames + 1) / 2; }   // fftfreq >= 0
 
@@ -603,10 +634,10 @@ struct PlanImpl {
     }
 
     void temporal_mean_spectrum(const float* maps, int n_frames, int rows, int cols, const float* first, float zero,
-                                int bs, int brows, int bcols, double* mean_host, int* valid_host, rt::stream_t s) {
+                                int bs, int brows, int bcols, int force_n1, double* mean_host, int* valid_host,
+                                rt::stream_t s) {
         temporal_geometry(rows, cols, bs, brows, bcols);
         if (n_frames < 2) rt::fail("temporal spectrum needs at least two frames");
-        temporal_tables(n_frames, s);
         const int nblk = brows * bcols, npos = temporal_npos(n_frames);
         t_mean.alloc((size_t)nblk * npos);
         t_valid.alloc((size_t)nblk);
@@ -614,14 +645,60 @@ struct PlanImpl {
         rt::dmemset(t_valid.ptr, 0, sizeof(int) * (size_t)nblk, s);
         const long long segs = (long long)bs * brows * bcols;
         launch<BlockValidCount>(blocks_for(segs), 1, s, BlockValidParams{first, t_valid.ptr, rows, cols, bs, brows, bcols, segs});
-        TemporalSpecParams p{maps, first, t_tw.ptr, t_chirp.ptr, t_bspec.ptr, t_mean.ptr, zero, n_frames, npos, rows, cols, bs, brows, bcols};
-        const bool blue = t_len != n_frames;
-        FCD_DISPATCH_L(t_len, {
-            constexpr int G = TuneT<L>::G;
-            if (bs % G != 0) rt::fail("temporal spectrum: the block size must be a multiple of 8");
-            if (blue) launch<TemporalSpectrum<L, G, true>>(bs * (bs / G), nblk, s, p);
-            else launch<TemporalSpectrum<L, G, false>>(bs * (bs / G), nblk, s, p);
-        })
+        int n1 = 0, n2 = 0;
+        if (force_n1 > 0) {                                    // tests: exercise the two-level path on short series
+            if (n_frames % force_n1 != 0) rt::fail("temporal spectrum: n1 does not divide the number of frames");
+            n1 = force_n1; n2 = n_frames / force_n1;
+        }
+        if (force_n1 <= 0 && temporal_length(n_frames) != 0) {
+            temporal_tables(n_frames, s);
+            TemporalSpecParams p{maps, first, t_tw.ptr, t_chirp_ptr, t_bspec_ptr, t_mean.ptr, zero, n_frames, npos, rows, cols, bs, brows, bcols};
+            const bool blue = t_len != n_frames;
+            FCD_DISPATCH_L(t_len, {
+                constexpr int G = TuneT<L>::G;
+                if (bs % G != 0) rt::fail("temporal spectrum: the block size must be a multiple of 8");
+                if (blue) launch<TemporalSpectrum<L, G, true>>(bs * (bs / G), nblk, s, p);
+                else launch<TemporalSpectrum<L, G, false>>(bs * (bs / G), nblk, s, p);
+            })
+        } else {
+            if (n1 == 0 && !temporal_split(n_frames, n1, n2))
+                rt::fail("temporal spectrum: the number of frames has no factorisation into two lengths <= 2048 "
+                         "(drop a frame or pass f0)");
+            const int l1 = bluestein_length(n1), l2 = bluestein_length(n2);
+            if (!l1 || !l2) rt::fail("temporal spectrum: factor too long");
+            build_blue(t_lvl[0], n1, l1, s);
+            build_blue(t_lvl[1], n2, l2, s);
+            if (t_twn_n != n_frames) {
+                std::vector<cf> h((size_t)n_frames);
+                for (int m = 0; m < n_frames; ++m) {
+                    const double ang = -2.0 * M_PI * (double)m / (double)n_frames;
+                    h[m] = mk<float>((float)std::cos(ang), (float)std::sin(ang));
+                }
+                t_twn.upload(h, s);
+                t_twn_n = n_frames;
+            }
+            // chunks of spatial blocks whose [N][pixels] complex workspace stays under 8 GB
+            const long long per_block = (long long)n_frames * bs * bs * (long long)sizeof(cf);
+            const int chunk_blocks = (int)std::max<long long>(1, std::min<long long>(nblk, (8LL << 30) / per_block));
+            t_ws.alloc((size_t)n_frames * chunk_blocks * bs * bs);
+            for (int b0 = 0; b0 < nblk; b0 += chunk_blocks) {
+                const int nb = std::min(chunk_blocks, nblk - b0);
+                TemporalTwoLevelParams p{maps, first, t_ws.ptr, nullptr, nullptr, nullptr, t_twn.ptr, t_mean.ptr, zero,
+                                         n_frames, n1, n2, npos, rows, cols, bs, brows, bcols, b0, nb * bs * bs};
+                p.tw = t_lvl[0].tw.ptr; p.chirp = t_lvl[0].chirp.ptr; p.bspec = t_lvl[0].bspec.ptr;
+                FCD_DISPATCH_L(l1, {
+                    constexpr int G = TuneT<L>::G;
+                    if (bs % G != 0) rt::fail("temporal spectrum: the block size must be a multiple of 8");
+                    launch<TemporalTwoLevel<L, G, 0>>(bs * (bs / G) * n2, nb, s, p);
+                })
+                p.tw = t_lvl[1].tw.ptr; p.chirp = t_lvl[1].chirp.ptr; p.bspec = t_lvl[1].bspec.ptr;
+                FCD_DISPATCH_L(l2, {
+                    constexpr int G = TuneT<L>::G;
+                    if (bs % G != 0) rt::fail("temporal spectrum: the block size must be a multiple of 8");
+                    launch<TemporalTwoLevel<L, G, 1>>(bs * (bs / G), nb * n1, s, p);
+                })
+            }
+        }
         rt::d2h(mean_host, t_mean.ptr, sizeof(double) * (size_t)nblk * npos, s);
         rt::d2h(valid_host, t_valid.ptr, sizeof(int) * (size_t)nblk, s);
         for (int b = 0; b < nblk; ++b)                                   // np.nanmean over the block's valid pixels
@@ -956,11 +1033,21 @@ int fcd_temporal_mean_spectrum(fcd_plan* plan, const float* maps_dev, int n_fram
     if (!plan || !maps_dev || !mean_out || !valid_out) { g_fcd_error = "null argument"; return FCD_ERR_INVALID; }
     return fcd_guard([&] {
         plan->impl.temporal_mean_spectrum(maps_dev, n_frames, rows, cols, first_map_dev, zero, block_size, block_rows,
-                                          block_cols, mean_out, valid_out, stream);
+                                          block_cols, 0, mean_out, valid_out, stream);
     });
 }
 
-int fcd_temporal_frames_supported(int n_frames) { return fcd::PlanImpl::temporal_length(n_frames) != 0; }
+int fcd_temporal_mean_spectrum_split(fcd_plan* plan, const float* maps_dev, int n_frames, int rows, int cols,
+                                     const float* first_map_dev, float zero, int block_size, int block_rows, int block_cols,
+                                     int n1, double* mean_out, int* valid_out, void* stream) {
+    if (!plan || !maps_dev || !mean_out || !valid_out || n1 < 1) { g_fcd_error = "bad argument"; return FCD_ERR_INVALID; }
+    return fcd_guard([&] {
+        plan->impl.temporal_mean_spectrum(maps_dev, n_frames, rows, cols, first_map_dev, zero, block_size, block_rows,
+                                          block_cols, n1, mean_out, valid_out, stream);
+    });
+}
+
+int fcd_temporal_frames_supported(int n_frames) { return fcd::PlanImpl::temporal_supported(n_frames) ? 1 : 0; }
 
 int fcd_temporal_accumulate(fcd_plan* plan, const float* maps_dev, int n_chunk, int t0, int n_total, int rows, int cols,
                             float zero, int block_size, int block_rows, int block_cols, const int* bins, int n_bins,

@@ -161,6 +161,139 @@ struct TemporalSpectrum {
     }
 };
 
+// ---- long series: N = N1 * N2 as two levels of chirp-convolution transforms ------------------------------------
+// X[k1 + N1 k2] = sum_{n2} W_N^{n2 k1} [ sum_{n1} x[n1 N2 + n2] W_N1^{n1 k1} ] W_N2^{n2 k2}
+// Stage 0: for every n2 a length-N1 transform over the frames n1*N2 + n2, times W_N^{n2 k1}, to a workspace
+//          ws[(k1*N2 + n2)][pixel of the chunk];  stage 1: for every k1 a length-N2 transform over n2 whose
+//          magnitudes go to mean[block][k1 + N1*k2].  A chunk is a range of spatial blocks whose N * pixels
+//          complex workspace fits the budget.  Both levels use Bluestein on a power-of-two length >= 2*Ni - 1.
+struct TemporalTwoLevelParams {
+    const float* maps;     // [N][H][W]
+    const float* first;    // [H][W] or null
+    cf* ws;                // [N][pixels of the chunk]
+    const cf* tw;          // engine twiddles of this stage's length L
+    const cf* chirp;       // [Ni]  exp(+i pi m^2 / Ni)
+    const cf* bspec;       // [L]
+    const cf* twn;         // [N]   exp(-2 pi i m / N)
+    double* mean;          // [blocks][npos]
+    float zero;
+    int N, N1, N2, npos, H, W, bs, brows, bcols;
+    int b0;                // first spatial block of the chunk
+    int chunk_pixels;      // pixels per frame in the workspace = blocks in chunk * bs * bs
+};
+
+template <int L, int G, int STAGE>
+struct TemporalTwoLevel {
+    using FF = Fft<L, -1, float>;
+    using FI = Fft<L, +1, float>;
+    using Params = TemporalTwoLevelParams;
+    static constexpr bool BLOCKED_TILES = true;
+    static constexpr bool PIPELINED = true;
+    static constexpr int SYNC_THREADS = 0;
+    static constexpr int MIN_BLOCKS = 1;
+    static constexpr int TPF = L / 16, THREADS = G * TPF, PHASES = 8;
+    static constexpr int STRIDE = GroupLayout<L, G>::STRIDE;
+    using TW = SmemTwiddles<FF, THREADS>;
+    static constexpr int SMEM_BYTES = TW::TW_BYTES + G * STRIDE * (int)sizeof(cf);
+    FCD_HD static void prologue(const Params& p, int tid, unsigned char* smem) { TW::load(p.tw, tid, smem); }
+    template <int PH, class P> FCD_HD static bool enabled(const P&, const unsigned char*, int) { return true; }
+    struct State { cf v[16]; double acc[16]; TileLink link; };
+
+    // stage 0 tiles: bx = pixel tile + tiles_per_block * n2, by = block of the chunk
+    // stage 1 tiles: bx = pixel tile,                         by = block of the chunk * N1 + k1
+    FCD_HD static void decode(const Params& p, int bx, int by, int g, int& blk, int& other, long long& px, int& pc) {
+        const int tpb = p.bs * (p.bs / G);                  // pixel tiles per spatial block
+        const int ptile = STAGE == 0 ? bx % tpb : bx;
+        other = STAGE == 0 ? bx / tpb : by % p.N1;          // n2 (stage 0) or k1 (stage 1)
+        const int brel = STAGE == 0 ? by : by / p.N1;
+        blk = p.b0 + brel;
+        const int tiles_per_row = p.bs / G;
+        const int r = (blk / p.bcols) * p.bs + ptile / tiles_per_row;
+        const int c = (blk % p.bcols) * p.bs + (ptile % tiles_per_row) * G + g;
+        px = (long long)r * p.W + c;
+        pc = brel * p.bs * p.bs + ptile * G + g;
+    }
+
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem_all, State& st) {
+        const cf* tw = reinterpret_cast<const cf*>(smem_all);
+        const int g = tid % G, t = tid / G;
+        cf* s = reinterpret_cast<cf*>(smem_all + TW::TW_BYTES) + g * STRIDE;
+        const int M = STAGE == 0 ? p.N1 : p.N2;             // this stage's transform length
+        int blk, other; long long px; int pc;
+        decode(p, bx, by, g, blk, other, px, pc);
+        if constexpr (PH == 0) {
+            if (st.link.first) {
+                FCD_UNROLL
+                for (int m = 0; m < 16; ++m) st.acc[m] = 0.0;
+            }
+            const long long plane = (long long)p.H * p.W;
+            FCD_UNROLL
+            for (int m = 0; m < 16; ++m) {
+                const int sidx = t + TPF * m;
+                cf a = mk<float>(0.f, 0.f);
+                if (sidx < M) {
+                    if constexpr (STAGE == 0) {
+                        const float x = p.maps[((long long)sidx * p.N2 + other) * plane + px] - p.zero;
+                        a = scale(conj(p.chirp[sidx]), x);
+                    } else {
+                        a = p.ws[((long long)other * p.N2 + sidx) * p.chunk_pixels + pc] * conj(p.chirp[sidx]);
+                    }
+                }
+                st.v[m] = a;
+            }
+            FF::stepA(st.v, t, s);
+        } else if constexpr (PH == 1) {
+            FF::stepB(st.v, t, s, tw);
+        } else if constexpr (PH == 2) {
+            FF::stepC(st.v, t, s);
+        } else if constexpr (PH == 3) {
+            FF::stepD(st.v, t, s, tw);
+            FCD_UNROLL
+            for (int m = 0; m < 16; ++m) st.v[m] = st.v[m] * p.bspec[t + TPF * m];
+        } else if constexpr (PH == 4) {
+            FI::stepA(st.v, t, s);
+        } else if constexpr (PH == 5) {
+            FI::stepB(st.v, t, s, tw);
+        } else if constexpr (PH == 6) {
+            FI::stepC(st.v, t, s);
+        } else {
+            FI::stepD(st.v, t, s, tw);
+            if constexpr (STAGE == 0) {
+                FCD_UNROLL
+                for (int m = 0; m < 16; ++m) {
+                    const int k1 = t + TPF * m;
+                    if (k1 < p.N1) {
+                        const cf y = st.v[m] * conj(p.chirp[k1]);
+                        const long long q = ((long long)other * k1) % p.N;
+                        p.ws[((long long)k1 * p.N2 + other) * p.chunk_pixels + pc] = y * p.twn[q];
+                    }
+                }
+            } else {
+                const bool valid = p.first == nullptr || p.first[px] != 0.0f;
+                FCD_UNROLL
+                for (int m = 0; m < 16; ++m) {
+                    const int k2 = t + TPF * m;
+                    const long long k = (long long)other + (long long)p.N1 * k2;
+                    if (valid && k2 < p.N2 && k < p.npos) {
+                        const cf x = st.v[m] * conj(p.chirp[k2]);
+                        st.acc[m] += (double)sqrtf(x.x * x.x + x.y * x.y);
+                    }
+                }
+                if (!st.link.has_next || st.link.next_by != by) {      // leaving this (block, k1): flush
+                    FCD_UNROLL
+                    for (int m = 0; m < 16; ++m) {
+                        const long long k = (long long)other + (long long)p.N1 * (t + TPF * m);
+                        if (t + TPF * m < p.N2 && k < p.npos && st.acc[m] != 0.0)
+                            atomic_add_f64(p.mean + (long long)blk * p.npos + k, st.acc[m]);
+                        st.acc[m] = 0.0;
+                    }
+                }
+            }
+        }
+    }
+};
+
 // number of valid pixels (first map != 0) per spatial block
 struct BlockValidParams {
     const float* first;   // may be null: every pixel valid

@@ -39,6 +39,10 @@ PROTOTYPES = {
                                                   ctypes.c_void_p, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                   c_double_p, c_int_p, ctypes.c_void_p]),
     "fcd_temporal_frames_supported": (ctypes.c_int, [ctypes.c_int]),
+    "fcd_temporal_mean_spectrum_split": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                                        ctypes.c_int, ctypes.c_void_p, ctypes.c_float, ctypes.c_int,
+                                                        ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p, c_int_p,
+                                                        ctypes.c_void_p]),
     "fcd_temporal_accumulate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int,
                                                ctypes.c_int, c_int_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,

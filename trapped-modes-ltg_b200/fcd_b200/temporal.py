@@ -91,8 +91,8 @@ def mean_spectra(maps: torch.Tensor, first_map: Optional[torch.Tensor], zero: fl
     device-resident stack [N, rows, cols] -> (numpy [blocks, npos], valid-pixel counts)."""
     n, rows, cols = (int(s) for s in maps.shape)
     if not plan.lib.fcd_temporal_frames_supported(n):
-        raise ValueError(f"f0 estimation needs a frame count that is a power of two in [64, 4096] or <= 2048 (got {n}); "
-                         "pass f0 explicitly for longer series")
+        raise ValueError(f"f0 estimation needs a frame count that is a power of two <= 4096, at most 2048, or a product of "
+                         f"two factors <= 2048 (got {n}); drop a frame or pass f0 explicitly")
     nblk = block_rows * block_cols
     npos = n // 2 if n % 2 == 0 else (n + 1) // 2
     mean = np.zeros((nblk, npos), np.float64)
