@@ -546,7 +546,7 @@ struct PlanImpl {
     const cf* t_bspec_ptr = nullptr;
     int t_twn_n = 0;
     rt::DevBuf<double> t_mean, t_twd;
-    rt::DevBuf<int> t_valid;
+    rt::DevBuf<int> t_valid, t_bins;
 
     static int temporal_length(int n_frames) {        // single-level transform length; 0: needs the two-level path
         if (n_frames >= 64 && n_frames <= 4096 && (n_frames & (n_frames - 1)) == 0) return n_frames;
@@ -713,17 +713,11 @@ struct PlanImpl {
         if (n_bins < 1 || n_bins > kMaxHarmonicBins) rt::fail("temporal harmonics: 1..8 bins per block");
         if (n_chunk < 0 || t0 < 0 || n_total < 1 || t0 + n_chunk > n_total) rt::fail("temporal harmonics: bad frame range");
         const int nblk = brows * bcols;
-        std::vector<double> tw((size_t)std::max(n_chunk, 1) * nblk * n_bins * 2);
-        for (int f = 0; f < n_chunk; ++f)
-            for (int b = 0; b < nblk; ++b)
-                for (int j = 0; j < n_bins; ++j) {
-                    const long long q = ((long long)bins[b * n_bins + j] * (t0 + f)) % n_total;    // exact phase reduction
-                    const double ang = 2.0 * M_PI * (double)q / (double)n_total;
-                    double* w = &tw[(((size_t)f * nblk + b) * n_bins + j) * 2];
-                    w[0] = std::cos(ang);
-                    w[1] = -std::sin(ang);
-                }
-        t_twd.upload(tw, s);
+        std::vector<int> hb(bins, bins + (size_t)nblk * n_bins);
+        t_bins.upload(hb, s);
+        const long long ntw = (long long)std::max(n_chunk, 1) * nblk * n_bins;
+        t_twd.alloc((size_t)ntw * 2);
+        launch<HarmonicTwiddles>(blocks_for(ntw), 1, s, HarmonicTwParams{t_bins.ptr, t_twd.ptr, n_chunk, nblk, n_bins, t0, n_total, (long long)n_chunk * nblk * n_bins});
         const long long total = (long long)rows * cols;
         const HarmonicAccParams hp{maps, t_twd.ptr, acc, zero, n_chunk, n_bins, rows, cols, bs, brows, bcols, init, total};
         switch (n_bins) {
@@ -736,7 +730,6 @@ struct PlanImpl {
             case 7: launch<HarmonicAccumulate<7>>(blocks_for(total), 1, s, hp); break;
             default: launch<HarmonicAccumulate<8>>(blocks_for(total), 1, s, hp); break;
         }
-        rt::sync(s);    // t_twd is reused by the next call
     }
 
     void temporal_finalize(const double* acc, int n_bins, int n_total, int rows, int cols, const float* first,

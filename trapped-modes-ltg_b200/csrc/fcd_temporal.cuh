@@ -23,6 +23,8 @@
 
 namespace fcd {
 
+constexpr double kPiT = 3.14159265358979323846;
+
 FCD_HD double nan_f64() {
     union { unsigned long long u; double d; } c;
     c.u = 0x7ff8000000000000ull;
@@ -328,6 +330,28 @@ struct HarmonicAccParams {
     int nf, nb, H, W, bs, brows, bcols, init;
     long long total;      // H * W
 };
+// cos / -sin of 2 pi k t / N for every (frame of the chunk, block, bin), phase reduced exactly in integers
+struct HarmonicTwParams {
+    const int* bins;      // [blocks][nb] (device)
+    double* tw;           // [nf][blocks][nb][2]
+    int nf, nblk, nb, t0, n_total;
+    long long total;      // nf * blocks * nb
+};
+struct HarmonicTwiddles : ElemBase {
+    using Params = HarmonicTwParams;
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
+        const long long i = (long long)bx * THREADS + tid;
+        if (i >= p.total) return;
+        const int per = p.nblk * p.nb;
+        const int f = (int)(i / per), bj = (int)(i % per);
+        const long long q = ((long long)p.bins[bj] * (p.t0 + f)) % p.n_total;
+        const double ang = 2.0 * kPiT * (double)q / (double)p.n_total;
+        p.tw[2 * i] = cos(ang);
+        p.tw[2 * i + 1] = -sin(ang);
+    }
+};
+
 struct alignas(16) dbl2 { double c, s; };
 template <int NB>
 struct HarmonicAccumulate : ElemBase {
