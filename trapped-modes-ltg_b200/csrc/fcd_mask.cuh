@@ -262,10 +262,6 @@ FCD_HD void uf_unite(int* L, int a, int b) {
     }
 }
 
-// LabelFlatten walks a line in segments of kLabelSeg pixels, one thread each (a whole line per thread
-// leaves the device mostly idle).
-constexpr int kLabelSeg = 64;
-
 struct LabelInitParams {
     const float* smooth;      // mode 0: foreground = smooth < sum[frame] / n
     const float* sums;        // [frames] pairwise float32 sums
@@ -428,7 +424,7 @@ struct RootStatsInit : ElemBase {
 struct LabelFlattenParams {
     int* L;
     RegionStats st;
-    long long n_rows;       // frames * H * (W / kLabelSeg): one thread per line segment
+    long long n_rows;       // frames * H lines, one warp each (32 * n_rows threads)
     int H, W;
     int with_bbox;
 };
@@ -449,10 +445,69 @@ struct LabelFlatten : ElemBase {
     template <int PH>
     FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
         const long long item = (long long)bx * THREADS + tid;
-        if (item >= p.n_rows) return;
-        const int segs = p.W / kLabelSeg;                       // a power of two
-        const long long row = item >> ilog2_pow2(segs);
-        const int cbeg = (int)(item & (segs - 1)) * kLabelSeg;
+#if defined(__CUDA_ARCH__)
+        // One warp per line, 32 consecutive pixels per step (coalesced).  The first lane of every stretch of
+        // equal labels finds the root and hands it to its stretch; statistics are flushed once per stretch
+        // of equal roots inside the word.
+        const long long row = item >> 5;
+        const int lane = (int)(item & 31);
+        if (row >= p.n_rows) return;                            // whole warps (THREADS % 32 == 0)
+        const int n = p.H * p.W;
+        const long long fo = (row >> ilog2_pow2(p.H)) * n;
+        const int r = (int)(row & (p.H - 1));
+        int* L = p.L + fo;
+        const unsigned below = (2u << lane) - 1u;               // lanes 0 .. lane
+        // a stretch that reaches the end of its word is carried (warp-uniform) into the next word and merged
+        // there if the line goes on with the same root: one flush per run and line, not one per word
+        int k_root = -1, k_cnt = 0, k_first = 0;
+        long long k_sc = 0;
+        for (int c0 = 0; c0 < p.W; c0 += 32) {
+            const int px = r * p.W + c0 + lane;
+            const int lab = L[px];
+            const bool fg = lab >= 0;
+            const int prev = __shfl_up_sync(0xffffffffu, lab, 1);
+            const bool lead = fg && (lane == 0 || prev != lab);
+            const unsigned leaders = __ballot_sync(0xffffffffu, lead);
+            int root = lead ? uf_find(L, px) : 0;
+            const unsigned mine = leaders & below;
+            root = __shfl_sync(0xffffffffu, root, mine ? 31 - __clz(mine) : 0);
+            // other rows may be reading L[px] while walking to their roots: writing the root keeps
+            // every chain valid (a root points at itself)
+            if (fg) L[px] = root;
+            const unsigned fgbits = __ballot_sync(0xffffffffu, fg);
+            const int rprev = __shfl_up_sync(0xffffffffu, root, 1);
+            const bool rlead = fg && (lane == 0 || !((fgbits >> (lane - 1)) & 1u) || rprev != root);
+            const unsigned stops = __ballot_sync(0xffffffffu, rlead) | ~fgbits;      // a stretch ends before any of these
+            const unsigned above = lane == 31 ? 0u : (stops >> (lane + 1));
+            const int len = above ? __ffs(above) : 32 - lane;                        // stretch length inside this word
+            int cnt = len, first = c0 + lane;
+            long long sc = (long long)len * first + (long long)len * (len - 1) / 2;
+            // lane 0 takes over the carried stretch if the line continues with the same root, else flushes it
+            const int root0 = __shfl_sync(0xffffffffu, root, 0);
+            const bool cont = k_cnt > 0 && (fgbits & 1u) && root0 == k_root;
+            if (lane == 0) {
+                if (cont) { cnt += k_cnt; first = k_first; sc += k_sc; }
+                else if (k_cnt > 0) flush(p, fo, k_root, r, k_cnt, k_first, k_first + k_cnt - 1, k_sc);
+            }
+            const bool reach = rlead && lane + len == 32;
+            const unsigned rb = __ballot_sync(0xffffffffu, reach);
+            if (rlead && !reach) flush(p, fo, root, r, cnt, first, first + cnt - 1, sc);
+            if (rb) {
+                const int src = __ffs(rb) - 1;
+                k_root = __shfl_sync(0xffffffffu, root, src);
+                k_cnt = __shfl_sync(0xffffffffu, cnt, src);
+                k_first = __shfl_sync(0xffffffffu, first, src);
+                k_sc = __shfl_sync(0xffffffffu, sc, src);
+            } else {
+                k_cnt = 0;
+            }
+        }
+        if (lane == 0 && k_cnt > 0) flush(p, fo, k_root, r, k_cnt, k_first, k_first + k_cnt - 1, k_sc);
+#else
+        // sequential emulation: lane 0 of every emulated warp walks the whole line
+        if ((item & 31) != 0) return;
+        const long long row = item >> 5;
+        if (row >= p.n_rows) return;
         const int n = p.H * p.W;
         const long long fo = (row >> ilog2_pow2(p.H)) * n;
         const int r = (int)(row & (p.H - 1));
@@ -460,7 +515,7 @@ struct LabelFlatten : ElemBase {
         int cur_root = -1, cnt = 0, c0 = 0, c1 = 0;
         long long sc = 0;
         int run_label = -2, run_root = -1;
-        for (int c = cbeg; c < cbeg + kLabelSeg; ++c) {
+        for (int c = 0; c < p.W; ++c) {
             const int px = r * p.W + c;
             const int lab = L[px];
             if (lab < 0) { run_label = -2; continue; }
@@ -468,8 +523,6 @@ struct LabelFlatten : ElemBase {
                 run_label = lab;
                 run_root = uf_find(L, px);
             }
-            // other rows may be reading L[px] while walking to their roots: writing the root keeps
-            // every chain valid (a root points at itself)
             L[px] = run_root;
             if (run_root != cur_root) {
                 flush(p, fo, cur_root, r, cnt, c0, c1, sc);
@@ -478,6 +531,7 @@ struct LabelFlatten : ElemBase {
             ++cnt; c1 = c; sc += c;
         }
         flush(p, fo, cur_root, r, cnt, c0, c1, sc);
+#endif
     }
 };
 

@@ -751,7 +751,6 @@ struct PlanImpl {
     rt::DevBuf<unsigned long long> m_sums, m_best;
 
     static int blocks_for(long long total) { return (int)((total + 255) / 256); }
-    long long nsegs(int nf) const { return (long long)nf * H * (W / kLabelSeg); }    // line segments of the labelling kernels
 
     void mask_workspace(bool with_stats) {
         const size_t n = (size_t)H * W, c = (size_t)mask_chunk();
@@ -799,7 +798,7 @@ struct PlanImpl {
             rt::dmemset(m_best.ptr, 0, sizeof(unsigned long long) * (size_t)nf, s);
             RegionStats st{m_area.ptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
             launch<RootStatsInit>(blocks_for(total), 1, s, RootStatsInitParams{m_L.ptr, st, total, (int)n, 0});
-            launch<LabelFlatten>(blocks_for(nsegs(nf)), 1, s, LabelFlattenParams{m_L.ptr, st, nsegs(nf), H, W, 0});
+            launch<LabelFlatten>(blocks_for(32LL * nf * H), 1, s, LabelFlattenParams{m_L.ptr, st, (long long)nf * H, H, W, 0});
             launch<LargestRegion>(blocks_for(total), 1, s, LargestParams{m_L.ptr, st, m_best.ptr, total, H, W, 0});
             launch<MaskOut>(blocks_for(total), 1, s, MaskOutParams{m_L.ptr, m_best.ptr, mask_out + f0 * n, total, (int)n});
         }
@@ -817,7 +816,7 @@ struct PlanImpl {
             int* minr = m_bbox.ptr; int* maxr = minr + total; int* minc = maxr + total; int* maxc = minc + total;
             RegionStats st{m_area.ptr, minr, maxr, minc, maxc, m_sums.ptr, m_sums.ptr + total};
             launch<RootStatsInit>(blocks_for(total), 1, s, RootStatsInitParams{m_L.ptr, st, total, (int)n, 1});
-            launch<LabelFlatten>(blocks_for(nsegs(nf)), 1, s, LabelFlattenParams{m_L.ptr, st, nsegs(nf), H, W, 1});
+            launch<LabelFlatten>(blocks_for(32LL * nf * H), 1, s, LabelFlattenParams{m_L.ptr, st, (long long)nf * H, H, W, 1});
             launch<LargestRegion>(blocks_for(total), 1, s, LargestParams{m_L.ptr, st, m_best.ptr, total, H, W, 1});
             launch<CenterOut>(blocks_for(nf), 1, s, CenterOutParams{m_best.ptr, st, m_centers.ptr, nf, (int)n});
             rt::d2h(centers_host + 2 * f0, m_centers.ptr, sizeof(int) * 2 * (size_t)nf, s);
