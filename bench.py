@@ -208,8 +208,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{n}x{n} synthetic checkerboard frames, one reference (BASELINE configs[1] shape)",
-                       "frames_per_step": procs, "size": n},
+            # the same workload as the CUDA arm (its `config`), each step a bounded sample of it
+            "config": {"workload": f"batch of {args.frames} frames {n}x{n} float32 per GPU, one reference "
+                                   f"(BASELINE.json configs[1])", "frames_per_gpu": args.frames, "size": n,
+                       "sample_frames_per_step": procs, "unwrap": True},
             "mpix_per_s": fps * n * n / 1e6,
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": procs, "kind": "port", "sample": sample,
                              "host_cpu_count": cores},
