@@ -32,7 +32,7 @@ template <> struct Tune<1024> { static constexpr int GROW = 4,  GCOL = 4,  GDEM 
 #define FCD_T2048_GCOL 4
 #endif
 #ifndef FCD_T2048_GDEM
-#define FCD_T2048_GDEM 2
+#define FCD_T2048_GDEM 4
 #endif
 template <> struct Tune<2048> { static constexpr int GROW = FCD_T2048_GROW, GCOL = FCD_T2048_GCOL, GDEM = FCD_T2048_GDEM, GGEN = 2; };
 template <> struct Tune<4096> { static constexpr int GROW = 2,  GCOL = 2,  GDEM = 2,  GGEN = 2; };
