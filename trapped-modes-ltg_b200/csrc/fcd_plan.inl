@@ -24,7 +24,10 @@ template <> struct Tune<64>   { static constexpr int GROW = 16, GCOL = 16, GDEM 
 template <> struct Tune<128>  { static constexpr int GROW = 8,  GCOL = 8,  GDEM = 8,  GGEN = 8; };
 template <> struct Tune<256>  { static constexpr int GROW = 8,  GCOL = 8,  GDEM = 8,  GGEN = 8; };
 template <> struct Tune<512>  { static constexpr int GROW = 4,  GCOL = 4,  GDEM = 4,  GGEN = 4; };
-template <> struct Tune<1024> { static constexpr int GROW = 4,  GCOL = 4,  GDEM = 4,  GGEN = 4; };
+#ifndef FCD_T1024_GDEM
+#define FCD_T1024_GDEM 8
+#endif
+template <> struct Tune<1024> { static constexpr int GROW = 4,  GCOL = 4,  GDEM = FCD_T1024_GDEM,  GGEN = 4; };
 #ifndef FCD_T2048_GROW
 #define FCD_T2048_GROW 2
 #endif
