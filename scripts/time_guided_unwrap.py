@@ -9,8 +9,8 @@ from fcd_b200 import synthetic as o
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 dev = torch.device("cuda", 0)
-plan = fcd_b200.HeightMapPlan((n, n), 8, dev)
-ref, frames = make_frames_gpu(n, 8, SEED, dev, peak_range=(4.0, 5.0))
+plan = fcd_b200.HeightMapPlan((n, n), 16, dev)
+ref, frames = make_frames_gpu(n, 16, SEED, dev, peak_range=(4.0, 5.0))
 plan.bind(ref, square_size=o.board_square_size(n), height=1.0)
 noisy = frames + 0.25 * torch.randn_like(frames)
 for name, fr in (("clean", frames), ("noisy", noisy)):

@@ -467,7 +467,7 @@ struct PlanImpl {
     // ------------------------------------------------------------------ reliability-guided unwrap ----
     // skimage.restoration.unwrap_phase (pyfcd/fcd.py:119): see fcd_unwrap.cuh.  Boruvka rounds until
     // no component has an outgoing edge left; kUnwrapMaps maps share one round (one host sync each).
-    static constexpr int kUnwrapMaps = 8;
+    static constexpr int kUnwrapMaps = 16;
     rt::DevBuf<float> ph_ws;
     rt::DevBuf<double> u_rel, u_border;
     rt::DevBuf<po_t> u_po;
