@@ -51,6 +51,9 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=3, help="frames timed for the cpu_baseline object")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed frames (rank 0, CPU)")
+    ap.add_argument("--unwrap", default="auto", choices=["auto", "scan", "herraez", "off"],
+                    help="unwrap mode of the timed calls; auto = the drop-in's default (pyfcd/fcd.py:14,119)")
     ap.add_argument("--peak-px", type=float, nargs=2, default=[0.2, 0.8],
                     help="range of the peak displacement in pixels (SURVEY 8(d): 0.2-0.8; 4-5 exercises the unwrap path)")
     ap.add_argument("--no-cufft", action="store_true", help="skip the cuFFT-based comparison pipeline")
@@ -164,26 +167,49 @@ def _cpu_one(args):
     return float(hm[0, 0])
 
 
-def cpu_baseline_single(n, sample):
-    """cpu_baseline object: the oracle port, one process, scipy's default single FFT thread."""
+_HOISTED = None
+
+
+def _cpu_one_hoisted(args):
+    """SURVEY 8(d) variant (iii): per-reference work done once per worker process, frames fanned out."""
+    global _HOISTED
+    ref, frame, sq = args
     from oracle import fcd_oracle as o
-    ref, frames = cpu_frames(n, sample, SEED)
+    if _HOISTED is None:
+        _HOISTED = o.compute_carriers(ref.astype(np.float64), sq)
+    carriers, cal = _HOISTED
+    return float(o.height_map_from_carriers(frame, carriers, cal, 1.0)[0][0, 0])
+
+
+def check_and_time_on_cpu(ref, frames, maps, n, full):
+    """The checker leg.  `frames` are frames of the TIMED batch (copied back from the device) and `maps` the
+    height maps the timed steps produced for them: the oracle port recomputes them in float64 and the relative
+    L2 error goes into the JSON line (`parity`).  With `full` the same calls are timed as the `cpu_baseline`
+    object (one process, scipy's default single FFT thread, carriers recomputed per frame as the reference
+    does, fcd.py:27) plus SURVEY 8(d) variant (ii) (carriers hoisted)."""
+    from oracle import fcd_oracle as o
     sq = o.board_square_size(n)
-    _cpu_one((ref, frames[0], sq))  # warm (imports, compiles the unwrap helper)
+    o.unwrap_phase(np.zeros((4, 4)))  # build / load the C helper outside the timed region
+    errs = []
     t0 = time.perf_counter()
-    for i in range(sample):
-        _cpu_one((ref, frames[i], sq))
+    for fr, hm in zip(frames, maps):
+        want, _, _ = o.compute_height_map(ref, fr, sq, height=1.0)
+        errs.append(float(np.linalg.norm(hm.astype(np.float64) - want) / np.linalg.norm(want)))
     dt = time.perf_counter() - t0
-    # SURVEY 8(d) variant (ii): the same with the per-reference work (carriers, ccsgn) hoisted out of the loop
-    carriers, cal = o.compute_carriers(ref.astype(np.float64), sq)
-    t1 = time.perf_counter()
-    for i in range(sample):
-        o.height_map_from_carriers(frames[i], carriers, cal, 1.0)
-    dth = time.perf_counter() - t1
-    return {"value": sample / dt, "unit": "frames/s", "cores": 1, "kind": "port",
-            "sample": f"{sample} frames {n}x{n} float32->float64, fcd.compute_height_map as the reference calls it "
-                      f"(carriers recomputed per frame, Herraez unwrap), oracle/fcd_oracle.py",
-            "carriers_hoisted_value": sample / dth}
+    parity = {"rel_l2_max": max(errs), "frames": len(errs), "tolerance": 1e-4,
+              "against": "oracle/fcd_oracle.py (float64 port of pyfcd, Herraez unwrap) on the timed frames themselves"}
+    cpu = None
+    if full:
+        carriers, cal = o.compute_carriers(ref.astype(np.float64), sq)
+        t1 = time.perf_counter()
+        for fr in frames:
+            o.height_map_from_carriers(fr, carriers, cal, 1.0)
+        dth = time.perf_counter() - t1
+        cpu = {"value": len(frames) / dt, "unit": "frames/s", "cores": 1, "kind": "port",
+               "sample": f"{len(frames)} frames {n}x{n} of the timed batch, float32->float64, fcd.compute_height_map as the "
+                         f"reference calls it (carriers recomputed per frame, Herraez unwrap), oracle/fcd_oracle.py",
+               "carriers_hoisted_value": len(frames) / dth}
+    return parity, cpu
 
 
 def run_reference(args):
@@ -209,6 +235,12 @@ def run_reference(args):
         for _ in range(args.steps):
             pool.map(_cpu_one, work)
         dt = time.perf_counter() - t0
+        # variant (iii) beside it: carriers hoisted (once per worker), all cores -- what a careful user of the
+        # reference would run; reported, not the headline (the reference itself recomputes per frame)
+        pool.map(_cpu_one_hoisted, work)
+        t1 = time.perf_counter()
+        pool.map(_cpu_one_hoisted, work)
+        dth = time.perf_counter() - t1
     fps = procs * args.steps / dt
     sample = (f"{procs} frames {n}x{n} per step (one per worker process), fcd.compute_height_map as the reference "
               f"calls it, float64, oracle port of /root/reference/pyfcd")
@@ -218,10 +250,10 @@ def run_reference(args):
             # the same workload as the CUDA arm (its `config`), each step a bounded sample of it
             "config": {"workload": f"batch of {args.frames} frames {n}x{n} float32 per GPU, one reference "
                                    f"(BASELINE.json configs[1])", "frames_per_gpu": args.frames, "size": n,
-                       "sample_frames_per_step": procs, "unwrap": True},
+                       "sample_frames_per_step": procs, "unwrap": "skimage-style reliability-guided (Herraez), as fcd.py:119"},
             "mpix_per_s": fps * n * n / 1e6,
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": procs, "kind": "port", "sample": sample,
-                             "host_cpu_count": cores},
+                             "host_cpu_count": cores, "carriers_hoisted_all_cores_value": procs / dth},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), file=_JSON_OUT, flush=True)
@@ -281,8 +313,12 @@ def run_ours(args):
     out = torch.empty_like(frames)
     torch.cuda.synchronize()
 
+    # unwrap="auto" is what the drop-in's default unwrap=True runs (pyfcd/fcd.py:14,119): the scan path plus the
+    # per-frame may-wrap flag of the demodulation kernel, a residue count for flagged frames and the
+    # reliability-guided unwrap for frames that hold residues
+    mode = args.unwrap
     for _ in range(max(args.warmup, 3)):
-        plan.execute(frames, out=out)
+        plan.execute(frames, out=out, unwrap=mode)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -293,7 +329,7 @@ def run_ours(args):
     barrier()
     e0.record()
     for _ in range(args.steps):
-        plan.execute(frames, out=out)
+        plan.execute(frames, out=out, unwrap=mode)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -311,9 +347,29 @@ def run_ours(args):
     ms_max = float(t.item())
     value = world * F * args.steps / (ms_max * 1e-3)
 
-    # sanity: the timed output is a real height map (finite, zero mean, non-trivial)
+    auto_stats = {"flagged_frames": plan.last_flagged_frames, "guided_frames": len(plan.last_guided_frames)} \
+        if mode == "auto" else None
+    # sanity: the timed output is a real height map (finite, non-trivial); the oracle comparison is further down
     chk = out[:: max(1, F // 8)]
     assert bool(torch.isfinite(chk).all()) and float(chk.abs().max()) > 0
+    # frames of the timed batch and their timed outputs, for the oracle check on rank 0
+    pick = sorted({0, F // 2, F - 1})[: max(2, args.cpu_sample)] if F >= 3 else list(range(F))
+    picked_frames = [frames[i].cpu().numpy() for i in pick]
+    picked_maps = [out[i].cpu().numpy() for i in pick]
+
+    # sharded == single GPU, bitwise: every rank runs the same 4-frame probe and the results'
+    # checksums must be identical across ranks
+    sharded_bitwise = None
+    if world > 1:
+        _, probe = make_frames_gpu(n, 4, SEED - 1, dev, peak_range=tuple(args.peak_px))
+        pm = plan.execute(probe, unwrap=mode)
+        words = pm.view(torch.int32).to(torch.int64)
+        ck = torch.stack([words.sum(), (words * torch.arange(1, words.numel() + 1, device=dev).view(words.shape) % 1000003).sum()])
+        got = [torch.empty_like(ck) for _ in range(world)]
+        dist.all_gather(got, ck)
+        sharded_bitwise = all(bool(torch.equal(g, got[0])) for g in got)
+        assert sharded_bitwise, "ranks disagree on the same frames"
+        del probe, pm, words
 
     # ---- e2e: host pinned buffers through the public API, copies inside the timed region ----
     e2e = None
@@ -345,7 +401,7 @@ def run_ours(args):
                 main.wait_event(ev_in[b])
                 if ev_out[b] is not None:
                     main.wait_event(ev_out[b])            # D2H that last read this output buffer
-                plan.execute(d_in[b][: c1 - c0], out=d_out[b][: c1 - c0])
+                plan.execute(d_in[b][: c1 - c0], out=d_out[b][: c1 - c0], unwrap=mode)
                 ev_done[b] = torch.cuda.Event()
                 ev_done[b].record(main)
                 with torch.cuda.stream(s_out):
@@ -418,6 +474,15 @@ def run_ours(args):
                  "what": "same pipeline on cuFFT via torch.fft (fft2, 2x ifft2, packed fft2, ifft2) + torch elementwise",
                  "rel_l2_ours_vs_cufft": err}
         del cp, ref_out
+        # per stage: the cuFFT calls of K1..K5 alone (FFT-only floor of a cuFFT-based pipeline), us per frame
+        try:
+            from fcd_b200.cufft_compare import time_cufft_stages
+            cs = time_cufft_stages((n, n), plan.band_columns, frames=16 if n <= 2048 else 4)
+            cufft["stages_us_per_frame"] = cs
+            cufft["fft_only_floor_us_per_frame"] = sum(cs[k] for k in ("row_fwd", "col_band", "row_demod", "col_integrate", "row_inv"))
+            cufft["fft_only_floor_frames_per_s"] = 1e6 / cufft["fft_only_floor_us_per_frame"]
+        except Exception as exc:  # the comparator is optional
+            cufft["stages_us_per_frame"] = f"unavailable: {exc}"
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -441,19 +506,24 @@ def run_ours(args):
                     "pipeline_achieved_gbs": value / world * 8 * P / 1e9,
                     "pipeline_frac": value / world * 8 * P / 1e9 / peak,
                     "stage_us_per_frame": {k: (v[0] * 1e3 / v[2] if v[2] else 0.0) for k, v in stages.items()}}
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_baseline_single(n, args.cpu_sample)
+        parity, cpu = None, None
+        if not args.no_parity:
+            full = world == 1 and not args.no_cpu_baseline
+            k = len(picked_frames) if full else 2
+            parity, cpu = check_and_time_on_cpu(ref.cpu().numpy(), picked_frames[:k], picked_maps[:k], n, full)
+            parity["frame_indices"] = pick[:k]
+            assert parity["rel_l2_max"] < 1e-4, parity
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"batch of {F} frames {n}x{n} float32 per GPU, one reference "
                                        f"(BASELINE.json configs[1])", "frames_per_gpu": F, "size": n,
-                           "frames_per_launch": args.frames_per_launch, "unwrap": True, "peak_displacement_px": list(args.peak_px),
+                           "frames_per_launch": args.frames_per_launch, "unwrap": mode, "auto": auto_stats, "peak_displacement_px": list(args.peak_px),
                            "l2": f"inputs {F * P * 4 / 1e9:.1f} GB per step are larger than the 126 MB L2 (no flush needed)",
                            "calibration_factor": cal, "parallelism": f"frame-sharded x{world}, no hot-path collective"},
                 "mpix_per_s": value * P / 1e6, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cpu, "cufft_pipeline": cufft}
+                "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "sharded_bitwise": sharded_bitwise,
+                "cufft_pipeline": cufft}
         print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.barrier()

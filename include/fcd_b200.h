@@ -65,7 +65,12 @@ int fcd_bind_reference(fcd_plan* plan, const void* reference_dev, int reference_
  * (+ optional phases_dev[n][2][rows][cols] float32).  Replaces pyfcd/fcd.py:28-33:
  * fft2(displaced) -> compute_phases (fcd.py:104-120, incl. unwrap_phase when unwrap != 0:
  * 1 = row/column scan, exact where the wrapped phases have no residues and the fast path;
- * 2 = reliability-guided like scikit-image, see fcd_unwrap_phase)
+ * 2 = reliability-guided like scikit-image, see fcd_unwrap_phase;
+ * 3 = "auto", what the drop-in's unwrap=True runs: the scan path, during which the demodulation kernel flags
+ * every frame that has |phase| > pi/2 somewhere -- only those can hold a 2*pi jump, let alone a residue; the
+ * flagged frames get their wrapped phases materialised and their residues counted, and the frames that hold
+ * residues are redone exactly as mode 2 would; frames without residues keep the scan result, where every
+ * unwrapper yields the same integers.  fcd_last_auto reports what happened)
  * -> compute_displacement_field (fcd.py:123-138) -> -u/height -> integrate_in_fourier
  * (fourier.py:116-137).  Optional mask_dev (uint8, nonzero = masked): the frame is replaced
  * by the reference under the mask before the transform and the height map is zeroed under
@@ -81,6 +86,11 @@ int fcd_execute(fcd_plan* plan, const float* frames_dev, int n_frames, float* he
 int fcd_execute_typed(fcd_plan* plan, const void* frames_dev, int frame_dtype, int n_frames, float* height_dev,
                       float* phases_dev, const uint8_t* mask_dev, long long mask_stride, int unwrap,
                       void* stream);
+
+/* After fcd_execute(..., unwrap = 3): number of frames flagged for a second look, number of frames redone with the
+ * reliability-guided unwrap and (up to `capacity` of) their indices within that call.  Outputs may be NULL. */
+int fcd_last_auto(const fcd_plan* plan, long long* flagged_out, int* guided_count_out, int* guided_frames_out,
+                  int capacity);
 
 /* Change the effective height (pyfcd/fcd.py:16-25, :32) of a bound plan without redoing the
  * per-reference work. */

@@ -105,6 +105,13 @@ class EmulPlan:
                                                            stride, int(unwrap), None))
         return (out, ph) if phases else out
 
+    def last_auto(self):
+        """(frames flagged for a second look, indices of the frames redone reliability-guided) of the last unwrap=3 call."""
+        flagged, count = ctypes.c_longlong(0), ctypes.c_int(0)
+        idx = (ctypes.c_int * 4096)()
+        _native.check(self.lib, self.lib.fcd_last_auto(self.h, ctypes.byref(flagged), ctypes.byref(count), idx, 4096))
+        return int(flagged.value), [idx[i] for i in range(count.value)]
+
     def unwrap_phase(self, wrapped):
         w = np.ascontiguousarray(wrapped, dtype=np.float32)
         n = w.size // (self.shape[0] * self.shape[1])

@@ -249,10 +249,10 @@ def test_empty_batches_and_bad_modes():
     assert plan.structure_mask(np.zeros((0, 64, 64), np.float32)).shape == (0, 64, 64)
     assert plan.mask_center(np.zeros((0, 64, 64), np.uint8)) == []
     with pytest.raises(_native.FcdError) as e:
-        plan.execute(np.zeros((1, 64, 64), np.float32), unwrap=3)
+        plan.execute(np.zeros((1, 64, 64), np.float32), unwrap=4)
     assert e.value.code == _native.FCD_ERR_INVALID
     # the reference frame itself demodulates to a flat surface (zero phases), with every unwrap mode
-    for mode in (0, 1, 2):
+    for mode in (0, 1, 2, 3):
         h = plan.execute(ref.astype(np.float32), unwrap=mode)
         assert np.abs(h).max() < 1e-4
     plan.close()

@@ -183,6 +183,122 @@ def test_full_size_4096_properties(api):
     plan.close()
 
 
+def test_full_size_4096_vs_oracle(api):
+    """BASELINE.json configs[2] shape against the float64 oracle itself (one frame; the oracle takes ~20 s):
+    the 16x16x16 radix plan and its pruned first pass must land where 2048^2 does."""
+    torch = api["torch"]
+    n = 4096
+    ref, frames, _ = o.synthetic_frames(n, 1)
+    sq = o.board_square_size(n)
+    hmo, pho, calo = o.compute_height_map(ref, frames[0], sq, height=1.0)
+    plan = api["eng"].HeightMapPlan((n, n), 1)
+    assert plan.bind(ref, square_size=sq, height=1.0) == calo
+    fr = torch.from_numpy(frames[:1]).cuda()
+    for mode in ("auto", "scan", "herraez"):
+        hm, ph = plan.execute(fr, phases=True, unwrap=mode)
+        assert rel_l2(hm[0].cpu().numpy(), hmo) < 1e-5, mode
+        for i in range(2):
+            assert phase_dev(ph[0, i].cpu().numpy().astype(np.float64), pho[i]) < 1e-4
+    plan.close()
+
+
+def test_full_size_2048_masked_typed_auto_vs_oracle(api):
+    """2048^2 through the default mode of the drop-in (unwrap="auto") with everything on at once: 16-bit camera
+    frames widened in K1, a per-frame mask (reference substituted before, zeros after: analyze.py:231,255), one
+    clean frame, one wrapping frame, one noisy wrapping frame (residues -> reliability-guided)."""
+    torch = api["torch"]
+    n = 2048
+    ref, frames, _ = o.synthetic_frames(n, 1)
+    sq = o.board_square_size(n)
+    h, uy, ux = o.gaussian_bump_displacement(n, (900.0, 1100.0), 260.0, 4.5)
+    wrapping = o.rotated_board(n, uy=uy, ux=ux)
+    noisy = wrapping + 0.25 * np.random.default_rng(5).standard_normal((n, n)).astype(np.float32)
+    noisy[800:1000, 700:1100] = 0.5
+    stack = np.stack([frames[0], wrapping, noisy]).astype(np.float32)
+    # the camera's integers: the oracle gets exactly the values the device widens (load_image's astype, analyze.py:40)
+    cam = np.clip(np.rint(stack * 60000.0), 0, 65535).astype(np.uint16)
+    ref_cam = np.clip(np.rint(ref * 60000.0), 0, 65535).astype(np.uint16).astype(np.float32)
+    mask = np.zeros((3, n, n), bool)
+    mask[:, 1200:1500, 300:800] = True
+    mask[2, 100:180, :] = True
+    plan = api["eng"].HeightMapPlan((n, n), 2)
+    plan.bind(ref_cam, square_size=sq, height=1.0)
+    hm = plan.execute(torch.from_numpy(cam).cuda(), mask=torch.from_numpy(mask).cuda(), unwrap="auto").cpu().numpy()
+    assert 2 in plan.last_guided_frames and 0 not in plan.last_guided_frames and plan.last_flagged_frames >= 2
+    for i in range(3):
+        fr = np.where(mask[i], ref_cam, cam[i].astype(np.float32))
+        want, _, _ = o.compute_height_map(ref_cam, fr, sq, height=1.0)
+        want *= ~mask[i]
+        assert rel_l2(hm[i], want) < 1e-5, i
+        assert not hm[i][mask[i]].any()
+    plan.close()
+
+
+def test_drop_in_cache_survives_other_binds(api, golden):
+    """The drop-in keeps per-reference state between calls; any other bind of the shared plan (folder, batched
+    API, a direct bind) must invalidate it."""
+    ga = lambda k: golden[f"synth256_small.{k}"]
+    gb = lambda k: golden[f"synth256_wrap.{k}"]
+    fcd, eng = api["fcd"], api["eng"]
+    ref_a, sq_a = ga("ref"), float(ga("square_size"))
+    ref_b = np.roll(ga("ref"), 3, axis=1) * 0.9 + 0.02            # same carriers, different pixels / ccsgn
+    hm_a0, _, _ = fcd.compute_height_map(ref_a, ga("frame"), sq_a, height=1.0)
+    eng.compute_height_maps(ref_b, ga("frame")[None], sq_a, height=1.0, frames_per_launch=1)   # rebinds the cached plan
+    hm_a1, _, _ = fcd.compute_height_map(ref_a, ga("frame"), sq_a, height=1.0)
+    assert np.array_equal(hm_a0, hm_a1)
+    eng.get_plan((256, 256), 1).bind(ref_b, square_size=sq_a, height=1.0)                     # direct bind
+    hm_a2, _, _ = fcd.compute_height_map(ref_a, ga("frame"), sq_a, height=1.0)
+    assert np.array_equal(hm_a0, hm_a2)
+    # truthy non-bool `unwrap` means the reference's unwrapper (fcd.py:119 does `if unwrap:`)
+    hm_w, _, _ = fcd.compute_height_map(gb("ref"), gb("frame"), float(gb("square_size")), height=1.0, unwrap=np.True_)
+    hm_w1, _, _ = fcd.compute_height_map(gb("ref"), gb("frame"), float(gb("square_size")), height=1.0, unwrap=1)
+    assert np.array_equal(hm_w, hm_w1) and rel_l2(hm_w, gb("height_map")) < 1e-5
+
+
+def test_plot_helpers_run_with_a_stub_matplotlib(api, golden, monkeypatch):
+    """examples/fcd_example.py:21-22 call fcd.fft_peaks(reference) and compute_calibration_factor(..., plot=True).
+    matplotlib is not installed here; a recording stub shows that both run and draw what the reference draws
+    (pyfcd/fcd.py:90-99, 157-175: the chosen peaks and the candidate list)."""
+    import sys
+    import types
+    calls = []
+
+    class Rec:
+        def __init__(self, name):
+            self._n = name
+
+        def __getattr__(self, k):
+            def f(*a, **kw):
+                calls.append((self._n + "." + k, a, kw))
+                return (Rec("fig"), Rec("ax")) if k == "subplots" else None
+            return f
+
+    plt = types.ModuleType("matplotlib.pyplot")
+    rec = Rec("plt")
+    for name in ("subplots", "legend", "tight_layout", "show"):
+        setattr(plt, name, getattr(rec, name))
+    mpl = types.ModuleType("matplotlib")
+    mpl.pyplot = plt
+    monkeypatch.setitem(sys.modules, "matplotlib", mpl)
+    monkeypatch.setitem(sys.modules, "matplotlib.pyplot", plt)
+    g = lambda k: golden[f"synth256_small.{k}"]
+    ref = g("ref")
+    cal, peaks = api["fcd"].compute_calibration_factor(float(g("square_size")), ref, plot=True)
+    assert cal == float(g("cal")) and np.array_equal(np.array(peaks), g("pixels"))
+    assert any(c[0] == "ax.imshow" for c in calls) and any(c[0] == "plt.show" for c in calls)
+    calls.clear()
+    api["fcd"].fft_peaks(ref)
+    drawn = [c for c in calls if c[0] == "ax.plot"]
+    want = [tuple(p) for p in o.find_peak_locations(o.highpassed_spectrum(ref.astype(np.float64)),
+                                                    0.5 * o.highpassed_spectrum(ref.astype(np.float64)).max(), 4)]
+    assert [(c[1][1], c[1][0]) for c in drawn[:len(want)]] == want          # candidates in the reference's order
+    assert (drawn[-2][1][1], drawn[-2][1][0]) == tuple(g("pixels")[0])      # rightmost
+    assert (drawn[-1][1][1], drawn[-1][1][0]) == tuple(g("pixels")[1])      # perpendicular
+    shown = [c for c in calls if c[0] == "ax.imshow"][0][1][0]
+    spec = np.log1p(np.fft.fftshift(np.abs(np.fft.fft2(ref.astype(np.float64) - ref.astype(np.float64).mean()))))
+    assert np.allclose(shown, spec, rtol=1e-9, atol=1e-9)
+
+
 def test_mask_workflow(api, golden):
     g = lambda k: golden[f"synth256_small.{k}"]
     torch = api["torch"]

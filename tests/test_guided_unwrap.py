@@ -80,6 +80,42 @@ def test_emulated_pipeline_with_residues(golden):
     plan.close()
 
 
+def test_emulated_auto_mode_flags_probes_and_redoes_only_what_it_must(golden):
+    """unwrap = 3 inside the C ABI: a frame that cannot wrap is never looked at again, a frame that wraps without
+    residues is probed and keeps its scan result, a frame with residues ends up bit-identical to mode 2."""
+    from tests.emul_lib import EmulPlan
+    from tests.test_emulated_kernels import bind_like_reference
+    ref, noisy, sq = noisy_wrap_frame(golden)
+    wrapping = golden["synth256_wrap.frame"]                      # 4-5 px displacement: 2*pi jumps, no residues
+    flat = ref.astype(np.float32)                                 # the reference itself: zero phases
+    frames = np.stack([flat, noisy, wrapping, noisy, noisy, flat, wrapping])
+    plan = EmulPlan((256, 256), 4)                                # 7 frames, 4 per launch: two waves
+    bind_like_reference(plan, ref, sq)
+    h3, p3 = plan.execute(frames, phases=True, unwrap=3)
+    flagged, guided = plan.last_auto()
+    assert flagged == 5 and guided == [1, 3, 4]
+    h1, p1 = plan.execute(frames, phases=True, unwrap=1)
+    h2, p2 = plan.execute(frames, phases=True, unwrap=2)
+    for i in (0, 2, 5, 6):
+        assert np.array_equal(h3[i], h1[i]) and np.array_equal(p3[i], p1[i])
+    for i in (1, 3, 4):
+        assert np.array_equal(h3[i], h2[i]) and np.array_equal(p3[i], p2[i])
+    # without a phases buffer the same height maps come out, and a per-frame mask follows its frame
+    assert np.array_equal(plan.execute(frames, unwrap=3), h3)
+    mask = np.zeros(frames.shape, np.uint8)
+    mask[:, 100:140, 60:90] = 1
+    mask[3, 10:20, :] = 1
+    hm3 = plan.execute(frames, mask=mask, unwrap=3)
+    _, gm = plan.last_auto()
+    hm2 = plan.execute(frames, mask=mask, unwrap=2)
+    hm1 = plan.execute(frames, mask=mask, unwrap=1)
+    assert {1, 3, 4} <= set(gm) and not {0, 5} & set(gm)          # the mask edge adds residues to the wrapping frames
+    for i in range(7):
+        assert np.array_equal(hm3[i], hm2[i] if i in gm else hm1[i])
+        assert not hm3[i][mask[i] != 0].any()
+    plan.close()
+
+
 # ----------------------------------------------------------------------------- device
 @pytest.mark.gpu
 def test_gpu_unwrap_matches_oracle():

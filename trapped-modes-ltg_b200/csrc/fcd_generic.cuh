@@ -176,6 +176,27 @@ struct SumKernel : NoPrologue {
     }
 };
 
+// float64 image -> float32 copy (the reference image as the masked workflow substitutes it, analyze.py:231)
+struct NarrowParams {
+    const double* in;
+    float* out;
+    long long n;
+    int nblocks;
+};
+struct NarrowF64 : NoPrologue {
+    using Params = NarrowParams;
+    static constexpr bool BLOCKED_TILES = false;
+    static constexpr bool PIPELINED = false;
+    static constexpr int SYNC_THREADS = 0;
+    static constexpr int MIN_BLOCKS = 1;
+    static constexpr int THREADS = 256, PHASES = 1, SMEM_BYTES = 16;
+    struct State { int dummy; };
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
+        for (long long i = (long long)bx * THREADS + tid; i < p.n; i += (long long)p.nblocks * THREADS) p.out[i] = (float)p.in[i];
+    }
+};
+
 // shifted |F| with high-pass zeroing and global max (fourier.py:18-23,34-35).  Magnitudes of
 // columns beyond W/2 are mirrored from the computed half so that conjugate bins are exactly
 // equal, as scipy's Hermitian fill makes them.

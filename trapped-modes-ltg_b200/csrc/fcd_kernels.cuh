@@ -64,6 +64,40 @@ FCD_HD float fast_atan2f(float y, float x) {
     return copysignf(r, y);
 }
 
+// Both carriers of a pixel at once: the polynomial and the wrap run as packed FMUL2 / FFMA2 chains
+// (.x = carrier 0, .y = carrier 1), the range reduction and the quadrant fix-ups stay scalar (FMNMX,
+// MUFU, predicated FADD have no packed form).  Same arithmetic per lane as fast_atan2f + the scalar
+// wrap of RowDemod::demod (what tests/emul executes).   z0, z1: the two complex samples;  th: the
+// two reference angles;  returns (phi0, phi1) = -wrap(angle(z_i) + th_i)      (fcd.py:118)
+#if defined(FCD_PACKED_F32)
+__device__ __forceinline__ cf demod_pair(cf z0, cf z1, float th0, float th1) {
+    const float ax0 = fabsf(z0.x), ay0 = fabsf(z0.y), ax1 = fabsf(z1.x), ay1 = fabsf(z1.y);
+    const float mx0 = fmaxf(fmaxf(ax0, ay0), 1e-30f), mn0 = fminf(ax0, ay0);
+    const float mx1 = fmaxf(fmaxf(ax1, ay1), 1e-30f), mn1 = fminf(ax1, ay1);
+    const float2 a = __fmul2_rn(make_float2(mn0, mn1), make_float2(fast_rcp(mx0), fast_rcp(mx1)));
+    const float2 s = __fmul2_rn(a, a);
+    float2 r = make_float2(-0.004054565913975239f, -0.004054565913975239f);
+    r = __ffma2_rn(r, s, make_float2(0.021862953901290894f, 0.021862953901290894f));
+    r = __ffma2_rn(r, s, make_float2(-0.0559123195707798f, -0.0559123195707798f));
+    r = __ffma2_rn(r, s, make_float2(0.0964219719171524f, 0.0964219719171524f));
+    r = __ffma2_rn(r, s, make_float2(-0.1390862911939621f, -0.1390862911939621f));
+    r = __ffma2_rn(r, s, make_float2(0.19946566224098206f, 0.19946566224098206f));
+    r = __ffma2_rn(r, s, make_float2(-0.33329859375953674f, -0.33329859375953674f));
+    r = __ffma2_rn(r, s, make_float2(0.9999993443489075f, 0.9999993443489075f));
+    r = __fmul2_rn(r, a);
+    float r0 = r.x, r1 = r.y;
+    r0 = (ay0 > ax0) ? 1.57079632679489661923f - r0 : r0;
+    r1 = (ay1 > ax1) ? 1.57079632679489661923f - r1 : r1;
+    r0 = (z0.x < 0.f) ? 3.14159265358979323846f - r0 : r0;
+    r1 = (z1.x < 0.f) ? 3.14159265358979323846f - r1 : r1;
+    const float2 ang = __fadd2_rn(make_float2(copysignf(r0, z0.y), copysignf(r1, z1.y)), make_float2(th0, th1));
+    const float2 q = __fmul2_rn(ang, make_float2(kInvTwoPiF, kInvTwoPiF));
+    // 2 pi * rint(q) - ang as one FMA per lane, which is what the compiler contracts the scalar expression to
+    return cf_of(__ffma2_rn(make_float2(rintf(q.x), rintf(q.y)), make_float2(kTwoPiF, kTwoPiF),
+                            make_float2(-ang.x, -ang.y)));
+}
+#endif
+
 // common helpers -------------------------------------------------------------------------
 template <int L, int G, int BUFS = 1>
 struct GroupLayout {
@@ -445,6 +479,8 @@ struct RowDemodParams {
     int kc0[2];
     int x_ref;
     int unwrap;
+    int* frameflag;      // [F] or null: set to 1 for frames with |phi| > pi/2 somewhere (the only frames that can
+                         // hold a 2*pi jump, let alone a residue: unwrap "auto" looks no further at the others)
 };
 
 struct int2s { int a, b; };
@@ -607,12 +643,28 @@ struct RowDemod {
             load_theta(p, 0, y, t, c0);
             FI::stepD2(st.v, st.w, t, s0, s1, tw);
             load_theta(p, 1, y, t, c1);
+#if defined(FCD_PACKED_F32)
+            float big = 0.f;
+            FCD_UNROLL
+            for (int m = 0; m < 16; ++m) {
+                st.v[m] = demod_pair(st.v[m], st.w[m], c0[m], c1[m]);
+                big = fmaxf(big, fmaxf(fabsf(st.v[m].x), fabsf(st.v[m].y)));
+            }
+            if (big > 1.57079632679489661923f) {               // this row may contain 2*pi jumps
+                *flag = 1;
+                if (p.frameflag) p.frameflag[f] = 1;
+            }
+#else
             float ph0[16], ph1[16];
             const bool big0 = demod(c0, st.v, ph0);
             const bool big1 = demod(c1, st.w, ph1);
-            if (big0 || big1) *flag = 1;      // this row may contain 2*pi jumps
+            if (big0 || big1) {               // this row may contain 2*pi jumps
+                *flag = 1;
+                if (p.frameflag) p.frameflag[f] = 1;
+            }
             FCD_UNROLL
             for (int m = 0; m < 16; ++m) st.v[m] = mk<float>(ph0[m], ph1[m]);
+#endif
             // wrapped phase at the anchor column links the rows (RowLink)
             if (t == (p.x_ref % TPF)) {
                 const int mr = p.x_ref / TPF;
@@ -928,26 +980,29 @@ struct ColIntegrate : AllPhases {
         } else if constexpr (PH == 4) {
             FF::stepD2(st.va, st.v, t, s0, s1, tw);
             if (valid) {
-                const float kxv = p.kx[kc], kxa = p.kxq[kc], kxb = p.kxq[kcm];
+                // Folded coefficients of Phi0, Phi1 in hhat / i, Hermitian part:
+                //   aH = ((kxa - kxb) f1r - (kya - kyb) f1c) / (2 k^2) * scale,   bH = ((kya - kyb) f0c - (kxa - kxb) f0r) / (2 k^2) * scale
+                // with kxa / kxb = quirk-zeroed kx[kc] / kx[-kc] (fourier.py:89) and kya / kyb = quirk-zeroed ky[kr] / ky[-kr]
+                // (fourier.py:92).  kya - kyb = wy * ky[kr] with wy = 2 except on three rows: kr = H/2 (ky[-kr] = ky[kr]: 0),
+                // kr = H/2 + 1 (kya zeroed: 1), kr = H/2 - 1 (kyb zeroed: 1).  Rows are kr = t + TPF*m with t < TPF, so the
+                // exceptions are compile-time impossible except for m = 7, 8.
+                const float kxv = p.kx[kc];
+                const float hs = 0.5f * p.scale;
+                const float dkx = (p.kxq[kc] - p.kxq[kcm]) * hs;
+                const cf cx0 = mk<float>(dkx * p.f1r, -dkx * p.f0r);       // kx part of (aH, bH) * k^2
+                const cf cy = mk<float>(-p.f1c * hs, p.f0c * hs);           // (aH, bH) * k^2 per unit of (kya - kyb)
+                const float kx2 = kxv * kxv;
+                const float tf = (float)t;
                 FCD_UNROLL
                 for (int m = 0; m < 16; ++m) {
-                    const int kr = t + TPF * m;
-                    const cf p0 = st.va[m];                     // 2 * Phi0(k)
-                    const cf p1 = st.v[m];                      // 2 * Phi1(k)
-                    const float kyv = (float)(kr < H / 2 ? kr : kr - H) * p.dky;          // ky[kr]
-                    const float kya = (kr == H / 2 + 1) ? 0.f : kyv;                     // quirk-zeroed ky[kr]
-                    const float kym = (kr == H / 2) ? kyv : -kyv;                        // ky[-kr]
-                    const float kyb = (kr == H / 2 - 1) ? 0.f : kym;                     // quirk-zeroed ky[-kr]
-                    float k2 = kxv * kxv + kyv * kyv;
-                    if (kr == 0 && kc == 0) k2 = 1.f;
-                    const float ik2 = fast_rcp(k2);
-                    // a(k), a(-k) and b(k), b(-k): coefficients of Phi0, Phi1 in hhat / i
-                    const float a_p = kxa * p.f1r - kya * p.f1c, a_m = kxb * p.f1r - kyb * p.f1c;
-                    const float b_p = kya * p.f0c - kxa * p.f0r, b_m = kyb * p.f0c - kxb * p.f0r;
-                    const float aH = 0.5f * (a_p - a_m) * ik2 * p.scale;
-                    const float bH = 0.5f * (b_p - b_m) * ik2 * p.scale;
-                    const cf acc = mk<float>(aH * p0.x + bH * p1.x, aH * p0.y + bH * p1.y);
-                    st.v[m] = mul_pi(acc);
+                    const float kyv = (tf + (float)(TPF * m - (m >= 8 ? H : 0))) * p.dky;   // ky[kr], exact integer * dky
+                    float wy = 2.f;
+                    if (m == 8) wy = (t == 0) ? 0.f : ((t == 1) ? 1.f : 2.f);
+                    if (m == 7) wy = (t == TPF - 1) ? 1.f : 2.f;
+                    float k2 = kyv * kyv + kx2;
+                    if (m == 0) k2 = (t == 0 && kc == 0) ? 1.f : k2;                        // k2[0,0] = 1 (fourier.py:130)
+                    const cf ab = scale(axpy(wy * kyv, cy, cx0), fast_rcp(k2));            // (aH, bH)
+                    st.v[m] = mul_pi(lin2(ab.x, st.va[m], ab.y, st.v[m]));                 // i (aH 2Phi0 + bH 2Phi1)
                 }
             } else {
                 FCD_UNROLL

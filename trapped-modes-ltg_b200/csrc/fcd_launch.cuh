@@ -5,6 +5,7 @@
 //     phase and thread sequentially on the CPU.  TEST INFRASTRUCTURE ONLY (tests/emul); it
 //     exists because the build container has no GPU.  The product never loads it.
 #pragma once
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -22,6 +23,10 @@ namespace rt {
 using stream_t = void*;
 
 [[noreturn]] inline void fail(const std::string& what) { throw std::runtime_error(what); }
+// a failing CUDA runtime call (-> FCD_ERR_RUNTIME); everything else thrown through fail() is a bad argument
+struct cuda_error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
 
 #if defined(FCD_EMULATE)
 // ------------------------------------------------------------------ CPU emulation --------
@@ -36,6 +41,7 @@ inline void h2d(void* d, const void* h, size_t n, stream_t) { std::memcpy(d, h, 
 inline void d2h(void* h, const void* d, size_t n, stream_t) { std::memcpy(h, d, n); }
 inline void d2d(void* d, const void* s, size_t n, stream_t) { std::memmove(d, s, n); }
 inline void sync(stream_t) {}
+inline int sm_count() { return 148; }
 
 // Order in which the emulated threads of a block run inside one phase: 0 ascending, 1 descending,
 // 2 odd threads first.  Within a phase there is no barrier, so a correct kernel must give
@@ -94,7 +100,13 @@ inline void launch(int gx, int gy, stream_t, const typename K::Params& p) {
 #else
 // ------------------------------------------------------------------ CUDA -----------------
 inline void check(cudaError_t e, const char* what) {
-    if (e != cudaSuccess) fail(std::string(what) + ": " + cudaGetErrorString(e));
+    if (e != cudaSuccess) throw cuda_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+inline int sm_count() {
+    int dev = 0, sms = 0;
+    check(cudaGetDevice(&dev), "cudaGetDevice");
+    check(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute");
+    return sms;
 }
 inline void* dmalloc(size_t n) {
     void* p = nullptr;
@@ -170,18 +182,26 @@ __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) fcd_kernel(const __
 
 template <class K>
 inline void launch(int gx, int gy, stream_t s, const typename K::Params& p) {
-    static int resident = 0;   // per kernel instantiation: blocks that fit on the whole device
-    if (!resident) {
+    // Per kernel instantiation AND per device: blocks that fit on the whole device.  Function attributes
+    // (the shared-memory opt-in) belong to the device that is current when they are set, and one process
+    // may hold plans on several GPUs, so nothing here is cached across devices.
+    constexpr int kMaxDevices = 64;
+    static std::atomic<int> resident_of[kMaxDevices];
+    int dev = 0;
+    check(cudaGetDevice(&dev), "cudaGetDevice");
+    if (dev < 0 || dev >= kMaxDevices) fail("device ordinal out of range");
+    int resident = resident_of[dev].load(std::memory_order_acquire);
+    if (!resident) {    // racing first launches compute the same value; the attribute call is idempotent
         if (K::SMEM_BYTES > 48 * 1024)
             check(cudaFuncSetAttribute(fcd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES),
                   "cudaFuncSetAttribute(smem)");
-        int dev = 0, sms = 0, per_sm = 0;
-        check(cudaGetDevice(&dev), "cudaGetDevice");
+        int sms = 0, per_sm = 0;
         check(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute");
         check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fcd_kernel<K>, K::THREADS, K::SMEM_BYTES),
               "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
         if (per_sm < 1) fail("kernel does not fit on an SM");
         resident = sms * per_sm;
+        resident_of[dev].store(resident, std::memory_order_release);
     }
     const int ntiles = gx * gy;
     if (ntiles <= 0) return;
@@ -269,6 +289,7 @@ struct DevBuf {
         ptr = static_cast<T*>(dmalloc(n * sizeof(T)));
         count = n;
     }
+    void grow(size_t n) { if (n > count || !ptr) alloc(n); }   // never shrinks
     void upload(const std::vector<T>& h, stream_t s) {
         alloc(h.size());
         h2d(ptr, h.data(), h.size() * sizeof(T), s);

@@ -113,6 +113,7 @@ struct PlanImpl {
             rt::fail("unsupported shape: rows and cols must be powers of two in [64, 4096]");
         if (frames_per_launch < 1 || frames_per_launch > 16384) rt::fail("frames_per_launch out of range");
         H = rows; W = cols; chunk = frames_per_launch;
+        sms = rt::sm_count();
         FCD_DISPATCH_L(W, {
             tw_w_f.upload(Fft<L, -1, float>::make_table(), nullptr);
             tw_w_d.upload(Fft<L, -1, double>::make_table(), nullptr);
@@ -147,7 +148,8 @@ struct PlanImpl {
         })
     }
 
-    static int elem_blocks(long long n) { return (int)std::min<long long>((n + 255) / 256, 148 * 8); }
+    int sms = 148;   // multiprocessors of the plan's device (init)
+    int elem_blocks(long long n) const { return (int)std::min<long long>((n + 255) / 256, (long long)sms * 8); }
 
     // ------------------------------------------------------------------ carrier search ----
     double highpass_spectrum(const void* image, int is_f64, double* spectrum_out, rt::stream_t s) {
@@ -377,90 +379,181 @@ struct PlanImpl {
     }
 
     // ------------------------------------------------------------------ execute ----
+    // One wave of frames (at most `chunk`), as pointers to its first frame.  The workspaces w1..w4 hold the
+    // wave; `wf` offsets into them let the back half of the pipeline run on a sub-range of a wave.
+    struct Wave {
+        const void* fr; int kind; int nf;
+        float* ho; const uint8_t* mk; long long mask_stride;
+    };
+    float scale_demod() const { return (float)(1.0 / (2.0 * (double)H * (double)W)); }
+    float scale_int() const { return (float)(1.0 / (2.0 * height * det * (double)H * (double)W)); }
+
+    // K1 row forward, K2 column band-pass, K3 row demodulation (+ row unwrap when scan) -> w3, colphase, flags
+    void stage_front(const Wave& a, float* po, int scan, int* flags, rt::stream_t s) {
+        FCD_DISPATCH_L(W, {
+            constexpr int G = Tune<L>::GROW;
+            RowFwdParams p{a.fr, a.kind, nullptr, a.mk, a.mask_stride, w1.ptr, tw_w_f.ptr, H, ncp,
+                           {nc[0], nc[1]}, {c_lo[0] - W / 2, c_lo[1] - W / 2}};
+            p.reference = reference_f32();
+            launch<RowFwd<L, G>>(H / (2 * G), a.nf, s, p);
+        })
+        if (profiling) timer.mark(s, 0);
+        FCD_DISPATCH_L(H, {
+            constexpr int G = Tune<L>::GCOL;
+            ColBandParams p{w1.ptr, w2.ptr, tw_h_f.ptr, chord_lo.ptr, chord_hi.ptr, ncp, {nc[0], nc[1]}, scale_demod()};
+            launch<ColBand<L, G>>(ceil_div(ncp, G), a.nf * 2, s, p);
+        })
+        if (profiling) timer.mark(s, 1);
+        FCD_DISPATCH_L(W, {
+            constexpr int G = Tune<L>::GDEM;
+            RowDemodParams p{w2.ptr, theta.ptr, w3.ptr, colphase.ptr, po, tw_w_f.ptr, H, ncp,
+                             {nc[0], nc[1]}, {c_lo[0] - W / 2, c_lo[1] - W / 2}, W / 2, scan, flags};
+            bool pruned = false;
+            if constexpr (Plan<L>::R1 == 8) {
+                if (nc[0] <= L / 8 && nc[1] <= L / 8) {
+                    pruned = true;
+                    launch<RowDemod<L, G, true>>(a.nf, H / G, s, p);
+                }
+            }
+            if (!pruned) launch<RowDemod<L, G, false>>(a.nf, H / G, s, p);
+        })
+        if (profiling) timer.mark(s, 2);
+    }
+    // K3b: rows linked along the anchor column; materialised phases get their row offsets
+    void stage_link(int nf, float* po, int scan, rt::stream_t s) {
+        launch<RowLink>(2, nf, s, RowLinkParams{colphase.ptr, rowoff.ptr, H, H / 2, scan});
+        if (profiling) timer.mark(s, 3);
+        if (po && scan) {
+            launch<PhaseFix>(H, nf * 2, s, PhaseFixParams{po, rowoff.ptr, H, W});
+            if (profiling) timer.mark(s, 4);
+        }
+    }
+    // reliability-guided unwrap of the wrapped phases of frames [wf, wf + nf) of a wave, in place, then their
+    // forward row transform into w3 (what K3 does in the scan modes)
+    void stage_guided(float* po_wave, int wf, int nf, rt::stream_t s) {
+        const long long n = (long long)H * W;
+        float* po = po_wave + (long long)wf * 2 * n;
+        unwrap_maps(po, nf * 2, po, s);
+        if (profiling) timer.mark(s, 3);
+        FCD_DISPATCH_L(W, {
+            constexpr int G = Tune<L>::GROW;
+            launch<RowPhaseFwd<L, G>>(H / G, nf, s, RowPhaseFwdParams{po, w3.ptr + (size_t)wf * w3_blocks(W) * H * 4, tw_w_f.ptr, H});
+        })
+        if (profiling) timer.mark(s, 4);
+    }
+    // K4 column integration, K5 row inverse for frames [wf, wf + nf) of the wave `a`
+    void stage_back(const Wave& a, int wf, int nf, int scan, rt::stream_t s) {
+        const long long n = (long long)H * W;
+        FCD_DISPATCH_L(H, {
+            constexpr int G = Tune<L>::GCOL;
+            ColIntegrateParams p{w3.ptr + (size_t)wf * w3_blocks(W) * H * 4, rowoff.ptr + (size_t)wf * 2 * H, w4.ptr, tw_h_f.ptr,
+                                 kx.ptr, kxq.ptr, dky, W, w4p,
+                                 (float)f[0][0], (float)f[0][1], (float)f[1][0], (float)f[1][1], scale_int(), scan};
+            launch<ColIntegrate<L, G>>(ceil_div(W / 2 + 1, G), nf, s, p);
+        })
+        if (profiling) timer.mark(s, 5);
+        FCD_DISPATCH_L(W, {
+            constexpr int G = Tune<L>::GROW;
+            RowInvParams p{w4.ptr, a.ho + (long long)wf * n, a.mk ? a.mk + (long long)wf * a.mask_stride : nullptr,
+                           a.mask_stride, tw_w_f.ptr, H, w4p};
+            launch<RowInv<L, G>>(H / (2 * G), nf, s, p);
+        })
+        if (profiling) timer.mark(s, 6);
+    }
+    static Wave sub_wave(const Wave& a, int wf, int nf, long long n) {
+        const size_t px = a.kind == 0 ? 4 : (a.kind == 1 ? 1 : 2);
+        return Wave{static_cast<const unsigned char*>(a.fr) + (size_t)wf * n * px, a.kind, nf, a.ho + (long long)wf * n,
+                    a.mk ? a.mk + (long long)wf * a.mask_stride : nullptr, a.mask_stride};
+    }
+
+    // unwrap = 3 ("auto", the drop-in's unwrap=True): statistics of the last fcd_execute call
+    rt::DevBuf<int> frameflag, res_counts;
+    long long auto_flagged = 0;               // frames with |phi| > pi/2 somewhere (probed for residues)
+    std::vector<int> auto_guided;             // frames whose phases held residues (redone reliability-guided)
+    static constexpr int kProbe = 16;         // frames per residue probe (bounds the phase scratch)
+
+    // Frames [w0, w0 + a.nf) of the call: after the scan pass, look again at the frames K3 flagged.  Their wrapped
+    // phases are materialised (K1-K3 once more, into scratch), residues counted, and only frames that hold any
+    // are unwrapped along the reliability-guided tree and re-integrated -- bit for bit what unwrap = 2 does.
+    // A frame without residues keeps its scan result: there every unwrapper gives the same integers.
+    void auto_second_look(const Wave& a, int w0, float* po_user, rt::stream_t s) {
+        const long long n = (long long)H * W;
+        std::vector<int> flags((size_t)a.nf);
+        rt::d2h(flags.data(), frameflag.ptr, sizeof(int) * (size_t)a.nf, s);
+        int i = 0;
+        while (i < a.nf) {
+            if (!flags[i]) { ++i; continue; }
+            int j = i;
+            while (j < a.nf && flags[j] && j - i < kProbe) ++j;
+            const int m = j - i;                                  // run of flagged frames [i, j)
+            auto_flagged += m;
+            ph_ws.grow((size_t)kProbe * 2 * n);
+            if (profiling) timer.begin_chunk(s, m);
+            const Wave sub = sub_wave(a, i, m, n);
+            stage_front(sub, ph_ws.ptr, 0, nullptr, s);           // wrapped phases of the run -> scratch
+            res_counts.grow((size_t)2 * kProbe);
+            rt::dmemset(res_counts.ptr, 0, sizeof(int) * 2 * kProbe, s);
+            launch<ResidueCount>(H - 1, 2 * m, s, ResidueParams{ph_ws.ptr, res_counts.ptr, H, W});
+            int counts[2 * kProbe];
+            rt::d2h(counts, res_counts.ptr, sizeof(int) * (size_t)(2 * m), s);
+            int q = 0;
+            while (q < m) {
+                if (!(counts[2 * q] || counts[2 * q + 1])) { ++q; continue; }
+                int r = q;
+                while (r < m && (counts[2 * r] || counts[2 * r + 1])) ++r;
+                stage_guided(ph_ws.ptr, q, r - q, s);              // frames [q, r) of the run
+                stage_back(sub, q, r - q, 0, s);
+                if (po_user)
+                    rt::d2d(po_user + (long long)(i + q) * 2 * n, ph_ws.ptr + (long long)q * 2 * n,
+                            sizeof(float) * (size_t)(r - q) * 2 * n, s);
+                for (int k = q; k < r; ++k) auto_guided.push_back(w0 + i + k);
+                q = r;
+            }
+            i = j;
+        }
+    }
+
     void execute(const void* frames, int frame_kind, int n_frames, float* height_out, float* phases,
                  const uint8_t* mask, long long mask_stride, int unwrap, rt::stream_t s) {
         if (frame_kind < 0 || frame_kind > 2) rt::fail("frame dtype must be 0 (float32), 1 (uint8) or 2 (uint16)");
-        if (unwrap < 0 || unwrap > 2) rt::fail("unwrap must be 0 (off), 1 (scan) or 2 (reliability-guided)");
+        if (unwrap < 0 || unwrap > 3) rt::fail("unwrap must be 0 (off), 1 (scan), 2 (reliability-guided) or 3 (auto)");
         const size_t px = frame_kind == 0 ? 4 : (frame_kind == 1 ? 1 : 2);
         if (!bound) throw std::logic_error("fcd_execute called before fcd_bind_reference");
         if (n_frames < 0) rt::fail("negative frame count");
         if (det == 0.0) rt::fail("carriers are collinear (singular 2x2 system)");
         const long long n = (long long)H * W;
-        const float scale_demod = (float)(1.0 / (2.0 * (double)H * (double)W));
-        const float scale_int = (float)(1.0 / (2.0 * height * det * (double)H * (double)W));
+        auto_flagged = 0;
+        auto_guided.clear();
         for (int f0 = 0; f0 < n_frames; f0 += chunk) {
             const int nf = std::min(chunk, n_frames - f0);
-            const void* fr = static_cast<const unsigned char*>(frames) + (size_t)f0 * n * px;
-            float* ho = height_out + (long long)f0 * n;
+            const Wave a{static_cast<const unsigned char*>(frames) + (size_t)f0 * n * px, frame_kind, nf,
+                         height_out + (long long)f0 * n, mask ? mask + (long long)f0 * mask_stride : nullptr, mask_stride};
             float* po = phases ? phases + (long long)f0 * 2 * n : nullptr;
-            const uint8_t* mk_ = mask ? mask + (long long)f0 * mask_stride : nullptr;
             if (profiling) timer.begin_chunk(s, nf);
-            FCD_DISPATCH_L(W, {
-                constexpr int G = Tune<L>::GROW;
-                RowFwdParams p{fr, frame_kind, nullptr, mk_, mask_stride, w1.ptr, tw_w_f.ptr, H, ncp,
-                               {nc[0], nc[1]}, {c_lo[0] - W / 2, c_lo[1] - W / 2}};
-                p.reference = reference_f32();
-                launch<RowFwd<L, G>>(H / (2 * G), nf, s, p);
-            })
-            if (profiling) timer.mark(s, 0);
-            FCD_DISPATCH_L(H, {
-                constexpr int G = Tune<L>::GCOL;
-                ColBandParams p{w1.ptr, w2.ptr, tw_h_f.ptr, chord_lo.ptr, chord_hi.ptr, ncp, {nc[0], nc[1]}, scale_demod};
-                launch<ColBand<L, G>>(ceil_div(ncp, G), nf * 2, s, p);
-            })
-            if (profiling) timer.mark(s, 1);
             // unwrap: 0 none, 1 row/column scan (exact where the wrapped phases have no residues),
-            // 2 reliability-guided (Herraez et al., what skimage.restoration.unwrap_phase implements)
-            const bool guided = unwrap == 2;
-            if (guided && !po) {
-                ph_ws.alloc((size_t)chunk * 2 * n);
-                po = ph_ws.ptr;
-            }
-            const int scan = (unwrap && !guided) ? 1 : 0;
-            FCD_DISPATCH_L(W, {
-                constexpr int G = Tune<L>::GDEM;
-                RowDemodParams p{w2.ptr, theta.ptr, w3.ptr, colphase.ptr, po, tw_w_f.ptr, H, ncp,
-                                 {nc[0], nc[1]}, {c_lo[0] - W / 2, c_lo[1] - W / 2}, W / 2, scan};
-                bool pruned = false;
-                if constexpr (Plan<L>::R1 == 8) {
-                    if (nc[0] <= L / 8 && nc[1] <= L / 8) {
-                        pruned = true;
-                        launch<RowDemod<L, G, true>>(nf, H / G, s, p);
-                    }
+            // 2 reliability-guided (Herraez et al., what skimage.restoration.unwrap_phase implements),
+            // 3 scan, then 2 for the frames that hold residues
+            if (unwrap == 2) {
+                if (!po) {
+                    ph_ws.grow((size_t)chunk * 2 * n);
+                    po = ph_ws.ptr;
                 }
-                if (!pruned) launch<RowDemod<L, G, false>>(nf, H / G, s, p);
-            })
-            if (profiling) timer.mark(s, 2);
-            if (guided) {
-                unwrap_maps(po, nf * 2, po, s);                       // in place
-                if (profiling) timer.mark(s, 3);
-                FCD_DISPATCH_L(W, {
-                    constexpr int G = Tune<L>::GROW;
-                    launch<RowPhaseFwd<L, G>>(H / G, nf, s, RowPhaseFwdParams{po, w3.ptr, tw_w_f.ptr, H});
-                })
-                if (profiling) timer.mark(s, 4);
-            } else {
-                launch<RowLink>(2, nf, s, RowLinkParams{colphase.ptr, rowoff.ptr, H, H / 2, scan});
-                if (profiling) timer.mark(s, 3);
-                if (po && scan) {
-                    launch<PhaseFix>(H, nf * 2, s, PhaseFixParams{po, rowoff.ptr, H, W});
-                    if (profiling) timer.mark(s, 4);
-                }
+                stage_front(a, po, 0, nullptr, s);
+                stage_guided(po, 0, nf, s);
+                stage_back(a, 0, nf, 0, s);
+                continue;
             }
-            FCD_DISPATCH_L(H, {
-                constexpr int G = Tune<L>::GCOL;
-                ColIntegrateParams p{w3.ptr, rowoff.ptr, w4.ptr, tw_h_f.ptr, kx.ptr, kxq.ptr, dky, W, w4p,
-                                     (float)f[0][0], (float)f[0][1], (float)f[1][0], (float)f[1][1], scale_int,
-                                     scan};
-                launch<ColIntegrate<L, G>>(ceil_div(W / 2 + 1, G), nf, s, p);
-            })
-            if (profiling) timer.mark(s, 5);
-            FCD_DISPATCH_L(W, {
-                constexpr int G = Tune<L>::GROW;
-                RowInvParams p{w4.ptr, ho, mk_, mask_stride, tw_w_f.ptr, H, w4p};
-                launch<RowInv<L, G>>(H / (2 * G), nf, s, p);
-            })
-            if (profiling) timer.mark(s, 6);
+            const int scan = unwrap ? 1 : 0;
+            int* flags = nullptr;
+            if (unwrap == 3) {
+                frameflag.grow((size_t)chunk);
+                rt::dmemset(frameflag.ptr, 0, sizeof(int) * (size_t)nf, s);
+                flags = frameflag.ptr;
+            }
+            stage_front(a, po, scan, flags, s);
+            stage_link(nf, po, scan, s);
+            stage_back(a, 0, nf, scan, s);
+            if (unwrap == 3) auto_second_look(a, f0, po, s);
         }
     }
 
@@ -737,7 +830,8 @@ struct PlanImpl {
 
     void temporal_finalize(const double* acc, int n_bins, int n_total, int rows, int cols, const float* first,
                            double* amps, double* phases, rt::stream_t s) {
-        if (n_bins < 1 || n_bins > kMaxHarmonicBins || n_total < 1) rt::fail("temporal harmonics: bad arguments");
+        if (n_bins < 1 || n_bins > kMaxHarmonicBins || n_total < 1 || rows < 1 || cols < 1)
+            rt::fail("temporal harmonics: bad arguments (1..8 bins, positive frame count and map size)");
         const long long total = (long long)rows * cols;
         launch<HarmonicFinalize>(blocks_for(total), 1, s, HarmonicFinParams{acc, first, amps, phases, n_bins, n_total, total});
     }
@@ -854,10 +948,12 @@ static int fcd_guard(Fn&& fn) {
     } catch (const std::logic_error& e) {
         g_fcd_error = e.what();
         return FCD_ERR_STATE;
-    } catch (const std::runtime_error& e) {
+    } catch (const fcd::rt::cuda_error& e) {
         g_fcd_error = e.what();
-        const bool cuda = g_fcd_error.find("cuda") != std::string::npos || g_fcd_error.find("kernel launch") != std::string::npos;
-        return cuda ? FCD_ERR_RUNTIME : FCD_ERR_INVALID;
+        return FCD_ERR_RUNTIME;
+    } catch (const std::runtime_error& e) {      // rt::fail: bad argument / unsupported request
+        g_fcd_error = e.what();
+        return FCD_ERR_INVALID;
     } catch (const std::exception& e) {
         g_fcd_error = e.what();
         return FCD_ERR_RUNTIME;
@@ -926,11 +1022,9 @@ int fcd_bind_reference(fcd_plan* plan, const void* reference_dev, int reference_
             fcd::rt::sync(stream);
             im.ref_f32_valid = true;
         } else {
-            std::vector<double> h((size_t)n);
-            fcd::rt::d2h(h.data(), reference_dev, n * sizeof(double), stream);
-            std::vector<float> hf((size_t)n);
-            for (long long i = 0; i < n; ++i) hf[i] = (float)h[i];
-            fcd::rt::h2d(im.ref_f32.ptr, hf.data(), n * sizeof(float), stream);
+            const int nb = im.elem_blocks(n);
+            im.launch<fcd::NarrowF64>(nb, 1, stream, fcd::NarrowParams{static_cast<const double*>(reference_dev), im.ref_f32.ptr, n, nb});
+            fcd::rt::sync(stream);
             im.ref_f32_valid = true;
         }
     });
@@ -990,7 +1084,7 @@ int fcd_get_carrier_ccsgn(fcd_plan* plan, int carrier, void* ccsgn_dev, int as_c
             return;
         }
         im.masked_inverse(carrier, stream, nullptr);
-        const int nb = fcd::PlanImpl::elem_blocks(n);
+        const int nb = im.elem_blocks(n);
         im.launch<fcd::CcsgnStore>(nb, 1, stream,
                                    fcd::CcsgnStoreParams{im.tmp.ptr, nullptr, static_cast<fcd::cd*>(ccsgn_dev), nullptr, n, nb});
     });
@@ -1071,6 +1165,16 @@ int fcd_structure_mask(fcd_plan* plan, const float* frames_dev, int n_frames, in
 int fcd_mask_center(fcd_plan* plan, const uint8_t* mask_dev, int n_frames, int* centers_out, void* stream) {
     if (!plan || n_frames < 0 || (n_frames > 0 && (!mask_dev || !centers_out))) { g_fcd_error = "bad argument"; return FCD_ERR_INVALID; }
     return fcd_guard([&] { plan->impl.mask_center(mask_dev, n_frames, centers_out, stream); });
+}
+
+int fcd_last_auto(const fcd_plan* plan, long long* flagged_out, int* guided_count_out, int* guided_frames_out, int capacity) {
+    if (!plan || capacity < 0) { g_fcd_error = "bad argument"; return FCD_ERR_INVALID; }
+    const auto& im = plan->impl;
+    if (flagged_out) *flagged_out = im.auto_flagged;
+    if (guided_count_out) *guided_count_out = (int)im.auto_guided.size();
+    if (guided_frames_out)
+        for (int i = 0; i < capacity && i < (int)im.auto_guided.size(); ++i) guided_frames_out[i] = im.auto_guided[(size_t)i];
+    return FCD_OK;
 }
 
 long long fcd_launch_count(const fcd_plan* plan) { return plan ? plan->impl.launches : 0; }

@@ -362,7 +362,13 @@ struct HarmonicAccumulate : ElemBase {
         const long long i = (long long)bx * THREADS + tid;
         if (i >= p.total) return;
         const int b = temporal_block_of((int)(i / p.W), (int)(i % p.W), p.bs, p.brows, p.bcols);
-        if (b < 0) return;
+        if (b < 0) {          // outside the block grid: nothing accumulates, but `init` still defines the sums
+            if (p.init) {
+                FCD_UNROLL
+                for (int j = 0; j < 2 * NB; ++j) p.acc[(long long)j * p.total + i] = 0.0;
+            }
+            return;
+        }
         double re[NB], im[NB];
         FCD_UNROLL
         for (int j = 0; j < NB; ++j) {

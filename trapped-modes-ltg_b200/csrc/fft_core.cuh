@@ -55,6 +55,42 @@ template <int DIR, class T> FCD_HD cx<T> rot(cx<T> a, T c, T s) {
     return DIR < 0 ? mk<T>(a.x * c + a.y * s, a.y * c - a.x * s) : mk<T>(a.x * c - a.y * s, a.y * c + a.x * s);
 }
 template <int DIR, class T> FCD_HD cx<T> mul_dir_i(cx<T> a) { return DIR < 0 ? mul_mi(a) : mul_pi(a); }
+// a * p + b * q with real a, b;   s * p + q with real s
+template <class T> FCD_HD cx<T> lin2(T a, cx<T> p, T b, cx<T> q) { return mk<T>(a * p.x + b * q.x, a * p.y + b * q.y); }
+template <class T> FCD_HD cx<T> axpy(T s, cx<T> p, cx<T> q) { return mk<T>(s * p.x + q.x, s * p.y + q.y); }
+
+// ---------------------------------------------------------------------------------------
+// sm_100a packed float32 arithmetic.  A complex64 value is an aligned register pair, and
+// FADD2 / FMUL2 / FFMA2 work on such pairs with free operand modifiers (swap halves, negate
+// one half, broadcast a scalar register / immediate), so a complex add is ONE instruction, a
+// complex multiply TWO (FMUL2 + FFMA2, the same roundings as the scalar FMUL + FFMA pair the
+// compiler contracts to) and a multiplication by +-i folds into the consuming add.  These
+// non-template overloads win over the generic templates for cx<float> in device code; the
+// CPU emulation (tests/emul) keeps the scalar templates.  -DFCD_NO_PACKED restores scalar
+// code on the device for A/B measurements.
+// ---------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000) && !defined(FCD_NO_PACKED)
+#define FCD_PACKED_F32 1
+__device__ __forceinline__ float2 f2_of(cf a) { return make_float2(a.x, a.y); }
+__device__ __forceinline__ cf cf_of(float2 a) { cf r; r.x = a.x; r.y = a.y; return r; }
+__device__ __forceinline__ cf operator+(cf a, cf b) { return cf_of(__fadd2_rn(f2_of(a), f2_of(b))); }
+__device__ __forceinline__ cf operator-(cf a, cf b) { return cf_of(__fadd2_rn(f2_of(a), make_float2(-b.x, -b.y))); }
+__device__ __forceinline__ cf operator*(cf a, cf b) {
+    // (a.x b.x - a.y b.y, a.y b.x + a.x b.y) = a * (b.x, b.x) + (a.y, a.x) * (-b.y, b.y)
+    const float2 t = __fmul2_rn(make_float2(a.y, a.x), make_float2(-b.y, b.y));
+    return cf_of(__ffma2_rn(f2_of(a), make_float2(b.x, b.x), t));
+}
+__device__ __forceinline__ cf scale(cf a, float s) { return cf_of(__fmul2_rn(f2_of(a), make_float2(s, s))); }
+__device__ __forceinline__ cf lin2(float a, cf p, float b, cf q) {
+    return cf_of(__ffma2_rn(f2_of(q), make_float2(b, b), __fmul2_rn(f2_of(p), make_float2(a, a))));
+}
+__device__ __forceinline__ cf axpy(float s, cf p, cf q) { return cf_of(__ffma2_rn(f2_of(p), make_float2(s, s), f2_of(q))); }
+template <int DIR> __device__ __forceinline__ cf rot(cf a, float c, float s) {
+    // a * (c + DIR * i * s)
+    const float2 t = __fmul2_rn(make_float2(a.y, a.x), DIR < 0 ? make_float2(s, -s) : make_float2(-s, s));
+    return cf_of(__ffma2_rn(f2_of(a), make_float2(c, c), t));
+}
+#endif
 
 // ---------------------------------------------------------------------------------------
 // in-register DFTs on strided slots v[0], v[S], ..., natural order in and out.

@@ -41,5 +41,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+CMP_LIB = os.path.join(PKG_DIR, "libfcd_cufft_compare.so")
+
+
+def build_cufft_compare(force: bool = False) -> str:
+    """Benchmark-only comparator (csrc/cufft_compare.cu, links cuFFT); the product library does not."""
+    src = os.path.join(CSRC, "cufft_compare.cu")
+    if not force and os.path.exists(CMP_LIB) and os.path.getmtime(CMP_LIB) >= os.path.getmtime(src):
+        return CMP_LIB
+    subprocess.check_call([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+                           "-shared", "-Xcompiler", "-fPIC", "-o", CMP_LIB, src, "-lcufft"])
+    return CMP_LIB
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))
+    print(build_cufft_compare(force=True))

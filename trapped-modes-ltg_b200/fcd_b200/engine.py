@@ -112,8 +112,9 @@ UNWRAP_MODES = {"off": 0, "scan": 1, "herraez": 2, "guided": 2, "auto": 3}
 def unwrap_mode(unwrap) -> int:
     """False / 'off' -> 0;  True / 'scan' -> 1 (row/column scan: the fast path, exact where the
     wrapped phases have no residues);  'herraez' -> 2 (reliability-guided, what
-    skimage.restoration.unwrap_phase does, pyfcd/fcd.py:119);  'auto' -> 3 (scan, then the frames
-    whose phases have residues are redone with 'herraez')."""
+    skimage.restoration.unwrap_phase does, pyfcd/fcd.py:119);  'auto' -> 3 (scan; the frames the
+    demodulation kernel flags as able to wrap get a residue count, and those that hold residues are
+    redone with 'herraez' -- all inside fcd_execute, include/fcd_b200.h)."""
     if isinstance(unwrap, str):
         try:
             return UNWRAP_MODES[unwrap]
@@ -143,6 +144,9 @@ class HeightMapPlan:
         self.calibration_factor = None
         self.height = None
         self._reference = None
+        self._dropin_key = None          # fcd.compute_height_map's reference cache (cleared by every bind)
+        self.last_guided_frames = []     # frames the last unwrap="auto" call redid reliability-guided
+        self.last_flagged_frames = 0     # frames that call looked at twice (|phase| > pi/2 somewhere)
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h:
@@ -199,6 +203,7 @@ class HeightMapPlan:
         Mirrors fcd.compute_carriers (fcd.py:54-70).  Returns the calibration factor."""
         ref = to_device_image(reference, self.device)
         self._check_image(ref)
+        self._dropin_key = None          # whatever was cached for the drop-in is gone from here on
         h_eff = resolve_height(layers, height)
         if peaks is None:
             peaks = self.find_peaks(ref)
@@ -246,6 +251,8 @@ class HeightMapPlan:
         if not (isinstance(frames, torch.Tensor) and frames.is_cuda and frames.dtype in kinds):
             raise TypeError("frames must be a CUDA float32 / uint8 / uint16 tensor "
                             "(see compute_height_maps for numpy input)")
+        if frames.device != self.device:
+            raise ValueError(f"frames are on {frames.device}, the plan is on {self.device}")
         kind = kinds[frames.dtype]
         squeeze = frames.dim() == 2
         fr = frames.unsqueeze(0) if squeeze else frames
@@ -254,13 +261,15 @@ class HeightMapPlan:
         n = fr.shape[0]
         if out is None:
             out = torch.empty(fr.shape, dtype=torch.float32, device=fr.device)
-        elif not (out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.numel() == fr.numel()):
-            raise ValueError("out must be a contiguous CUDA float32 tensor of the frames' size")
+        elif not (out.is_cuda and out.device == self.device and out.dtype == torch.float32 and out.is_contiguous()
+                  and out.numel() == fr.numel()):
+            raise ValueError("out must be a contiguous CUDA float32 tensor of the frames' size on the plan's device")
         ph = None
         if isinstance(phases, torch.Tensor):
             ph = phases
-            if not (ph.is_cuda and ph.dtype == torch.float32 and ph.is_contiguous() and ph.numel() == 2 * fr.numel()):
-                raise ValueError("phases must be a contiguous CUDA float32 tensor [n, 2, H, W]")
+            if not (ph.is_cuda and ph.device == self.device and ph.dtype == torch.float32 and ph.is_contiguous()
+                    and tuple(ph.shape) == (n, 2) + self.shape):
+                raise ValueError("phases must be a contiguous CUDA float32 tensor [n, 2, H, W] on the plan's device")
         elif phases:
             ph = torch.empty((n, 2) + self.shape, dtype=torch.float32, device=self.device)
         mask_stride = 0
@@ -273,47 +282,18 @@ class HeightMapPlan:
                 mask_stride = self.shape[0] * self.shape[1]
             self._check_image(mk)
         with torch.cuda.device(self.device):
-            if mode == 3:
-                self._execute_auto(fr, kind, out, ph, mk, mask_stride)
-            else:
-                check(self.lib, self.lib.fcd_execute_typed(self._h, _ptr(fr), kind, int(n), _ptr(out), _ptr(ph),
-                                                           _ptr(mk), int(mask_stride), mode, _stream_ptr()))
+            check(self.lib, self.lib.fcd_execute_typed(self._h, _ptr(fr), kind, int(n), _ptr(out), _ptr(ph),
+                                                       _ptr(mk), int(mask_stride), mode, _stream_ptr()))
+        if mode == 3:
+            flagged, count = ctypes.c_longlong(0), ctypes.c_int(0)
+            idx = (ctypes.c_int * max(int(n), 1))()
+            check(self.lib, self.lib.fcd_last_auto(self._h, ctypes.byref(flagged), ctypes.byref(count), idx, int(n)))
+            self.last_flagged_frames = int(flagged.value)
+            self.last_guided_frames = [idx[i] for i in range(count.value)]
         if squeeze:
             out = out.view(self.shape) if out.dim() == 3 else out
             ph = ph[0] if ph is not None else None
         return (out, ph) if ph is not None else out
-
-    def _execute_auto(self, fr, kind, out, ph, mk, mask_stride) -> None:
-        """Scan unwrap per chunk with the phases materialised, residue count per map, and the
-        reliability-guided unwrap for the frames that have residues (where the scan result
-        depends on the path and the reference's unwrapper has to be followed)."""
-        n, px = int(fr.shape[0]), self.shape[0] * self.shape[1]
-        out3 = out.view((n,) + self.shape)
-        step = self.frames_per_launch
-        scratch = None if ph is not None else torch.empty((min(step, n), 2) + self.shape, dtype=torch.float32,
-                                                           device=self.device)
-        self.last_guided_frames = []
-        for c0 in range(0, n, step):
-            c1 = min(n, c0 + step)
-            ph_c = ph[c0:c1] if ph is not None else scratch[:c1 - c0]
-            mk_c = None if mk is None else (mk[c0:c1] if mask_stride else mk)
-            check(self.lib, self.lib.fcd_execute_typed(self._h, _ptr(fr[c0:c1]), kind, c1 - c0, _ptr(out3[c0:c1]),
-                                                       _ptr(ph_c), _ptr(mk_c), int(mask_stride), 1, _stream_ptr()))
-            counts = (ctypes.c_int * (2 * (c1 - c0)))()
-            check(self.lib, self.lib.fcd_count_residues(self._h, _ptr(ph_c), 2 * (c1 - c0), counts, _stream_ptr()))
-            bad = [i for i in range(c1 - c0) if counts[2 * i] or counts[2 * i + 1]]
-            if not bad:
-                continue
-            self.last_guided_frames += [c0 + i for i in bad]
-            idx = torch.tensor(bad, device=self.device)
-            fr_b = fr[c0:c1].index_select(0, idx).contiguous()
-            out_b = torch.empty((len(bad),) + self.shape, dtype=torch.float32, device=self.device)
-            ph_b = torch.empty((len(bad), 2) + self.shape, dtype=torch.float32, device=self.device)
-            mk_b = None if mk is None else (mk[c0:c1].index_select(0, idx).contiguous() if mask_stride else mk)
-            check(self.lib, self.lib.fcd_execute_typed(self._h, _ptr(fr_b), kind, len(bad), _ptr(out_b), _ptr(ph_b),
-                                                       _ptr(mk_b), int(mask_stride), 2, _stream_ptr()))
-            out3[c0:c1].index_copy_(0, idx, out_b)
-            ph_c.index_copy_(0, idx, ph_b)
 
     def unwrap_phase(self, wrapped: torch.Tensor) -> torch.Tensor:
         """Reliability-guided unwrap of [..., H, W] float32 maps (skimage.restoration.unwrap_phase as

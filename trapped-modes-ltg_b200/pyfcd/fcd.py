@@ -26,7 +26,7 @@ class fcd:
         # frames with one reference (pydata/analyze.py:220-252), so the per-reference state is
         # kept while the reference pixels (compared on the device) and square_size are unchanged.
         ref_dev = _eng.to_device_image(reference, plan.device)
-        cached = getattr(plan, "_dropin_key", None)
+        cached = plan._dropin_key        # cleared by every HeightMapPlan.bind, whoever calls it
         if (cached is not None and cached[1] == float(square_size) and cached[0].dtype == ref_dev.dtype
                 and torch.equal(cached[0], ref_dev)):
             calibration_factor = plan.calibration_factor
@@ -37,7 +37,9 @@ class fcd:
             calibration_factor = plan.bind(ref_dev, square_size=square_size, height=height)
             plan._dropin_key = (ref_dev, float(square_size))
         frame = _eng.to_device_image(displaced, plan.device, allow_f64=False)
-        height_map, phases = plan.execute(frame, phases=True, unwrap="auto" if unwrap is True else unwrap)
+        # the reference does `if unwrap:` (fcd.py:119): any truthy non-string value means its unwrapper
+        mode = unwrap if isinstance(unwrap, str) else ("auto" if bool(unwrap) else False)
+        height_map, phases = plan.execute(frame, phases=True, unwrap=mode)
         return (height_map.to(torch.float64).cpu().numpy(), phases.to(torch.float64).cpu().numpy(),
                 calibration_factor)
 
