@@ -56,6 +56,8 @@ def parse_args():
                     help="unwrap mode of the timed calls; auto = the drop-in's default (pyfcd/fcd.py:14,119)")
     ap.add_argument("--peak-px", type=float, nargs=2, default=[0.2, 0.8],
                     help="range of the peak displacement in pixels (SURVEY 8(d): 0.2-0.8; 4-5 exercises the unwrap path)")
+    ap.add_argument("--no-residues", action="store_true", help="skip the all-residue (guided unwrap) leg")
+    ap.add_argument("--residue-frames", type=int, default=32)
     ap.add_argument("--no-cufft", action="store_true", help="skip the cuFFT-based comparison pipeline")
     ap.add_argument("--cufft-frames", type=int, default=64)
     return ap.parse_args()
@@ -384,13 +386,16 @@ def run_ours(args):
         s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
         main = torch.cuda.current_stream()
 
+        chunks = [(c0, min(E, c0 + c)) for c0 in range(0, E, c)]
+
         def e2e_step():
-            ev_in = [None, None]
-            ev_done = [None, None]
-            ev_out = [None, None]
-            k = 0
-            for c0 in range(0, E, c):
-                c1 = min(E, c0 + c)
+            # execute() in "auto" mode ends with a small device->host read (the may-wrap flags), so the host
+            # runs at most one chunk ahead of the device: the upload of chunk k+1 is queued BEFORE chunk k is
+            # executed, the download of chunk k right after -- both copy engines stay busy under the kernels.
+            ev_in, ev_done, ev_out = [None, None], [None, None], [None, None]
+
+            def upload(k):
+                c0, c1 = chunks[k]
                 b = k & 1
                 with torch.cuda.stream(s_in):
                     if ev_done[b] is not None:
@@ -398,9 +403,15 @@ def run_ours(args):
                     d_in[b][: c1 - c0].copy_(h_in[c0:c1], non_blocking=True)
                     ev_in[b] = torch.cuda.Event()
                     ev_in[b].record(s_in)
+
+            upload(0)
+            for k, (c0, c1) in enumerate(chunks):
+                b = k & 1
                 main.wait_event(ev_in[b])
                 if ev_out[b] is not None:
                     main.wait_event(ev_out[b])            # D2H that last read this output buffer
+                if k + 1 < len(chunks):
+                    upload(k + 1)                         # its buffer was last read by chunk k-1, already queued
                 plan.execute(d_in[b][: c1 - c0], out=d_out[b][: c1 - c0], unwrap=mode)
                 ev_done[b] = torch.cuda.Event()
                 ev_done[b].record(main)
@@ -409,7 +420,6 @@ def run_ours(args):
                     h_out[c0:c1].copy_(d_out[b][: c1 - c0], non_blocking=True)
                     ev_out[b] = torch.cuda.Event()
                     ev_out[b].record(s_out)
-                k += 1
             torch.cuda.synchronize()
 
         e2e_step()
@@ -448,6 +458,29 @@ def run_ours(args):
         e2e["copy_only_frames_per_s"] = E * args.e2e_steps / dtc
         e2e["copy_only_gbs_each_way"] = E * args.e2e_steps * P * 4 / dtc / 1e9
         e2e["frac_of_copy_bound"] = e2e["value"] / world / e2e["copy_only_frames_per_s"]
+
+    # ---- frames as a camera delivers them: noise and wrapping phases, residues in every map, so the drop-in's
+    # default mode sends every frame through the reliability-guided unwrap (pyfcd/fcd.py:119 on real images) ----
+    residue_leg = None
+    if rank == 0 and not args.no_residues:
+        nR = min(args.residue_frames, F)
+        _, rf = make_frames_gpu(n, nR, SEED + 7, dev, peak_range=(4.0, 5.0))
+        g = torch.Generator(device=dev).manual_seed(SEED)
+        rf += 0.25 * torch.randn(rf.shape, device=dev, generator=g)
+        out_r = torch.empty_like(rf)
+        plan.execute(rf, out=out_r, unwrap="auto")
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(3):
+            plan.execute(rf, out=out_r, unwrap="auto")
+        r1.record()
+        torch.cuda.synchronize()
+        residue_leg = {"value": 3 * nR / (r0.elapsed_time(r1) * 1e-3), "unit": "frames/s", "frames": nR,
+                       "flagged_frames": plan.last_flagged_frames, "guided_frames": len(plan.last_guided_frames),
+                       "what": "unwrap=auto on noisy wrapping frames (4-5 px displacement + 0.25 camera noise): every "
+                               "frame is flagged, probed for residues and redone reliability-guided"}
+        del rf, out_r
 
     # ---- the same pipeline on cuFFT (torch.fft) for comparison, bounded sample, rank 0 --------
     cufft = None
@@ -523,7 +556,7 @@ def run_ours(args):
                            "calibration_factor": cal, "parallelism": f"frame-sharded x{world}, no hot-path collective"},
                 "mpix_per_s": value * P / 1e6, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "sharded_bitwise": sharded_bitwise,
-                "cufft_pipeline": cufft}
+                "residue_leg": residue_leg, "cufft_pipeline": cufft}
         print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.barrier()

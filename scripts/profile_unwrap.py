@@ -22,5 +22,5 @@ t0 = time.perf_counter()
 for _ in range(reps):
     u = plan.unwrap_phase(w)
 torch.cuda.synchronize()
-dt = (time.perf_counter() - t0) / reps
+dt = (time.perf_counter() - t0) / max(reps, 1)
 print(f"unwrap {maps} maps {n}x{n}: {dt * 1e3:.2f} ms = {dt * 1e3 / maps:.3f} ms per map; residues of map 0: {plan.count_residues(w[:1])}")

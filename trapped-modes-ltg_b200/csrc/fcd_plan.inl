@@ -558,15 +558,16 @@ struct PlanImpl {
     }
 
     // ------------------------------------------------------------------ reliability-guided unwrap ----
-    // skimage.restoration.unwrap_phase (pyfcd/fcd.py:119): see fcd_unwrap.cuh.  Boruvka rounds until
-    // no component has an outgoing edge left; kUnwrapMaps maps share one round (one host sync each).
-    static constexpr int kUnwrapMaps = 16;
+    // skimage.restoration.unwrap_phase (pyfcd/fcd.py:119): see fcd_unwrap.cuh.  Boruvka rounds until no edge
+    // crosses two components; the maps of a wave share every launch.  One host read per round (the length of the
+    // next edge list = termination test and grid size); the kernels take the exact lengths from device counters.
+    int unwrap_wave_maps() const { return (int)std::max<long long>(1, std::min<long long>(16, (1LL << 26) / ((long long)H * W))); }
     rt::DevBuf<float> ph_ws;
     rt::DevBuf<double> u_rel, u_border;
     rt::DevBuf<po_t> u_po;
-    rt::DevBuf<unsigned long long> u_bw;
-    rt::DevBuf<unsigned> u_be;
-    rt::DevBuf<unsigned> u_counters, u_list[2], u_chosen;
+    rt::DevBuf<unsigned long long> u_bw, u_key[2];
+    rt::DevBuf<unsigned> u_be, u_counters, u_id[2], u_ru[2], u_rv[2], u_chosen;
+    rt::DevBuf<unsigned char> u_isroot;
     long long unwrap_rounds = 0;
 
     void unwrap_maps(const float* wrapped, int n_maps, float* out, rt::stream_t s) {
@@ -585,50 +586,53 @@ struct PlanImpl {
             }
             u_border.upload(b, s);
         }
-        const size_t cap = (size_t)kUnwrapMaps * n;
-        u_rel.alloc(cap); u_po.alloc(cap); u_bw.alloc(cap); u_be.alloc(cap); u_counters.alloc(4);
-        u_list[0].alloc(2 * cap); u_list[1].alloc(2 * cap); u_chosen.alloc(cap + 1024);
-        for (int m0 = 0; m0 < n_maps; m0 += kUnwrapMaps) {
-            const int nm = std::min(kUnwrapMaps, n_maps - m0);
+        const int wave = unwrap_wave_maps();
+        const size_t cap = (size_t)wave * n;
+        u_rel.grow(cap); u_po.grow(cap); u_bw.grow(cap); u_be.grow(cap); u_isroot.grow(cap); u_counters.grow(4);
+        u_chosen.grow(cap);                                   // at most one chosen edge per component
+        for (int k = 0; k < 2; ++k) {                         // a map has fewer than 2n edges
+            u_key[k].grow(2 * cap); u_id[k].grow(2 * cap); u_ru[k].grow(2 * cap); u_rv[k].grow(2 * cap);
+        }
+        for (int m0 = 0; m0 < n_maps; m0 += wave) {
+            const int nm = std::min(wave, n_maps - m0);
             const long long total = nm * n;
             const float* w = wrapped + m0 * n;
             launch<MstReliability>(blocks_for(total), 1, s, MstRelParams{w, u_border.ptr, u_rel.ptr, u_po.ptr, total, H, W});
-            MstRoundParams base{w, u_rel.ptr, u_po.ptr, u_bw.ptr, u_be.ptr, nullptr, nullptr, u_counters.ptr, total, H, W, nullptr};
-            const unsigned* list = nullptr;            // round 0: all 2n edges of every map, enumerated implicitly
-            long long count = 2 * total;
-            for (int round = 0; round < 64 && count > 0; ++round) {
-                rt::dmemset(u_counters.ptr, 0, 4 * sizeof(unsigned), s);
+            MstRoundParams base{w, u_rel.ptr, u_po.ptr, u_bw.ptr, u_be.ptr, EdgeList{}, EdgeList{}, u_chosen.ptr,
+                                u_counters.ptr, u_isroot.ptr, total, H, W, nullptr};
+            auto list_of = [&](int k) { return EdgeList{u_key[k].ptr, u_id[k].ptr, u_ru[k].ptr, u_rv[k].ptr}; };
+            // round 0: every pixel is a component (local minima, no unions), then the first list of cross edges
+            rt::dmemset(u_counters.ptr, 0, 4 * sizeof(unsigned), s);
+            launch<MstRound0>(blocks_for(total), 1, s, base);
+            launch<MstFlatten>(blocks_for(total), 1, s, base);
+            MstRoundParams bp = base;
+            bp.out = list_of(0);
+            launch<MstBuild>(blocks_for(total), 1, s, bp);
+            unsigned c[4];
+            rt::d2h(c, u_counters.ptr, sizeof(c), s);
+            ++unwrap_rounds;
+            long long count = c[1];
+            int cur = 0;
+            for (int round = 1; round < 64 && count > 0; ++round) {
+                // counters: [3] = length of this round's list, the others start from zero
+                const unsigned init[4] = {0u, 0u, 0u, (unsigned)count};
+                rt::h2d(u_counters.ptr, init, sizeof(init), s);
                 MstRoundParams rp = base;
-                rp.list = list; rp.count = count;
-                rp.list_out = u_chosen.ptr;
-                if (round == 0) {                       // every pixel is a component: local minima, no unions needed
-                    launch<MstRound0>(blocks_for(total), 1, s, base);
-                    launch<MstFlatten>(blocks_for(total), 1, s, base);
-                } else {
-                    launch<MstSelect<0>>(blocks_for(count), 1, s, rp);
-                    launch<MstSelect<1>>(blocks_for(count), 1, s, rp);
-                    launch<MstMark>(blocks_for(count), 1, s, rp);
-                    unsigned c[4];
-                    rt::d2h(c, u_counters.ptr, sizeof(c), s);
-                    const long long chosen = c[2];
-                    if (chosen == 0) break;             // no component has an outgoing edge left
-                    MstRoundParams up = base;
-                    up.list = u_chosen.ptr; up.count = chosen;
-                    launch<MstUnite>(blocks_for(chosen), 1, s, up);
-                    if (round < 2) launch<MstFlatten>(blocks_for(total), 1, s, base);   // still touches most pixels
-                }
-                unsigned* out_list = u_list[round & 1].ptr;
-                rp.list_out = out_list;
+                rp.in = list_of(cur); rp.out = list_of(cur ^ 1); rp.count = count;
+                launch<MstSelect<0>>(blocks_for(count), 1, s, rp);
+                launch<MstSelect<1>>(blocks_for(count), 1, s, rp);
+                launch<MstMark>(blocks_for(count), 1, s, rp);
+                launch<MstUnite>(blocks_for(std::min<long long>(count, total)), 1, s, rp);   // chosen <= components
                 launch<MstCompact>(blocks_for(count), 1, s, rp);
-                unsigned c[4];
                 rt::d2h(c, u_counters.ptr, sizeof(c), s);
                 ++unwrap_rounds;
-                list = out_list;
+                if (c[2] == 0 && c[1] != 0) rt::fail("unwrap: cross edges left but none selected");
                 count = c[1];
+                cur ^= 1;
             }
+            launch<MstFlattenRoots>(blocks_for(total), 1, s, base);
             MstRoundParams fp = base;
-            launch<MstFlatten>(blocks_for(total), 1, s, fp);
-            fp.out = out + m0 * n;
+            fp.outp = out + m0 * n;
             launch<MstApply>(blocks_for(total), 1, s, fp);
         }
     }

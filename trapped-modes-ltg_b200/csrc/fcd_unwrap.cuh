@@ -165,21 +165,34 @@ struct MstReliability : ElemBase {
 };
 
 // ---- Boruvka rounds over a shrinking list of cross edges -------------------------------------------------
-// Round 0 enumerates all 2n edges of every map implicitly; every later round works on the list of edges whose
-// end points still lie in different components (compacted after each round), so the work per round falls
-// with the number of component boundaries instead of staying at 2n.  A global edge id is map * 2n + e.
+// Round 0 is local (MstRound0: every pixel is a component and picks its minimum incident edge).  Every later
+// round works on the list of edges whose end points still lie in different components.  A list entry carries what
+// the round needs, so that the selection passes stream through the list without chasing a single pointer:
+//     key  bit pattern of rel[u] + rel[v] (a double >= 0: unsigned order == numeric order)
+//     id   global edge id  = map * 2n + e
+//     ru, rv   the ROOTS of the two end points, as global pixel indices (map * n + pixel)
+// Between the compaction that wrote the entry and the unions of the next round the union-find does not change, so
+// the cached roots are exact; the compaction after the unions re-finds them starting from the old roots (a chain as
+// long as the unions stacked in that one round) and drops the edges that have become internal.
+struct EdgeList {
+    unsigned long long* key;
+    unsigned* id;
+    unsigned* ru;
+    unsigned* rv;
+};
 struct MstRoundParams {
     const float* w;
     const double* rel;
-    po_t* PO;
-    unsigned long long* best_w;   // [maps][n] per root: smallest outgoing weight (bit pattern of a double >= 0)
-    unsigned* best_e;             // [maps][n] per root: smallest edge index among those of that weight
-    const unsigned* list;         // global edge ids of this round, or null: all edges 0 .. count-1
-    unsigned* list_out;           // MstCompact: surviving cross edges; MstMark: chosen edges
-    unsigned* counters;           // [0] merges, [1] length of list_out (MstCompact), [2] chosen (MstMark)
-    long long count;              // edges in this round (Select / Mark / Compact / ResetList), pixels (Reset, Flatten, Apply)
+    po_t* PO;                     // [maps][n]; parents are pixel indices WITHIN the map
+    unsigned long long* best_w;   // [maps][n] per root: smallest outgoing weight
+    unsigned* best_e;             // [maps][n] per root: smallest edge id among those of that weight
+    EdgeList in, out;             // this round's list / the list being written (MstBuild, MstCompact)
+    unsigned* chosen;             // MstMark -> MstUnite: ids of the edges some component selected
+    unsigned* counters;           // [0] merges, [1] length of `out`, [2] length of `chosen`, [3] length of `in`
+    unsigned char* isroot0;       // [maps][n] 1 for the roots of the round-0 forest (the only nodes later unions move)
+    long long count;              // upper bound of the items of this launch (the exact list lengths are counters)
     int H, W;
-    float* out;                   // MstApply
+    float* outp;                  // MstApply
 };
 FCD_HD unsigned atomic_add_u32(unsigned* a, unsigned v) {
 #if defined(__CUDA_ARCH__)
@@ -190,63 +203,17 @@ FCD_HD unsigned atomic_add_u32(unsigned* a, unsigned v) {
     return o;
 #endif
 }
-// (map, e, u, v) of item i of the round; false for the non-edges of the implicit enumeration
-FCD_HD bool mst_edge(const MstRoundParams& p, long long i, long long& map, int& e, int& u, int& v) {
-    const int n = p.H * p.W;
-    const long long g = p.list ? (long long)p.list[i] : i;
-    map = g / (2LL * n);
-    e = (int)(g - map * 2LL * n);
-    return edge_ends(e, n, p.H, p.W, u, v);
-}
-struct MstReset : ElemBase {
-    using Params = MstRoundParams;
-    template <int PH>
-    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
-        const long long i = (long long)bx * THREADS + tid;
-        if (i >= p.count) return;
-        p.best_w[i] = ~0ull;
-        p.best_e[i] = ~0u;
-    }
-};
-template <int PASS>   // 0: minimum weight per component, 1: minimum edge index among the minimum-weight edges
-struct MstSelect : ElemBase {
-    using Params = MstRoundParams;
-    template <int PH>
-    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
-        const long long i = (long long)bx * THREADS + tid;
-        if (i >= p.count) return;
-        long long map; int e, u, v;
-        if (!mst_edge(p, i, map, e, u, v)) return;
-        const long long o = map * p.H * p.W;
-        int ru, rv, t0, t1;
-        pot_find(p.PO + o, u, ru, t0);
-        pot_find(p.PO + o, v, rv, t1);
-        if (ru == rv) return;
-        const unsigned long long key = f64_bits(p.rel[o + u] + p.rel[o + v]);
-        unsigned long long* bw = p.best_w + o;
-        if (PASS == 0) {
-            atomic_min_u64(bw + ru, key);
-            atomic_min_u64(bw + rv, key);
-        } else {
-            unsigned* be = p.best_e + o;
-            if (bw[ru] == key) atomic_min_u32(be + ru, (unsigned)e);
-            if (bw[rv] == key) atomic_min_u32(be + rv, (unsigned)e);
-        }
-    }
-};
-// block-aggregated append: one global atomic per thread block
-struct AppendState { unsigned value; int keep; unsigned slot; };
-template <class K>
-FCD_HD void block_append(int ph, int tid, unsigned char* smem, AppendState& st, unsigned* list_out, unsigned* counter) {
+// block-aggregated append of up to two items per thread: one global atomic per thread block
+struct AppendState { unsigned n; unsigned slot; };
+FCD_HD void block_append_reserve(int ph, int tid, unsigned char* smem, AppendState& st, unsigned* counter) {
     unsigned* sc = reinterpret_cast<unsigned*>(smem);        // [0] block count, [1] block base
     if (ph == 0) { if (tid == 0) sc[0] = 0; }
-    else if (ph == 1) { if (st.keep) st.slot = atomic_add_u32(sc, 1u); }
+    else if (ph == 1) { if (st.n) st.slot = atomic_add_u32(sc, st.n); }
     else if (ph == 2) { if (tid == 0) sc[1] = atomic_add_u32(counter, sc[0]); }
-    else { if (st.keep) list_out[sc[1] + st.slot] = st.value; }
+    else { st.slot += sc[1]; }
 }
 struct MstListBase : ElemBase {
     static constexpr int PHASES = 4, SMEM_BYTES = 16;
-    struct State { AppendState a; };
 };
 // Round 0: every pixel is its own component, so its minimum outgoing edge is the minimum over its (at most four)
 // incident edges under the same (weight, edge index) order.  The picks form a forest once every mutual pick
@@ -291,72 +258,6 @@ struct MstRound0 : ElemBase {
         p.PO[o + px] = po_pack(q, off);
     }
 };
-// edges that some component selected as its minimum (evaluated while PO is not being modified)
-struct MstMark : MstListBase {
-    using Params = MstRoundParams;
-    template <int PH>
-    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem, State& st) {
-        if constexpr (PH == 1) {
-            st.a.keep = 0;
-            const long long i = (long long)bx * THREADS + tid;
-            long long map; int e, u, v;
-            if (i < p.count && mst_edge(p, i, map, e, u, v)) {
-                const long long o = map * p.H * p.W;
-                int ru, rv, t0, t1;
-                pot_find(p.PO + o, u, ru, t0);
-                pot_find(p.PO + o, v, rv, t1);
-                if (ru != rv && (p.best_e[o + ru] == (unsigned)e || p.best_e[o + rv] == (unsigned)e)) {
-                    st.a.keep = 1;
-                    st.a.value = (unsigned)(map * 2LL * p.H * p.W + e);
-                }
-            }
-        }
-        block_append<MstMark>(PH, tid, smem, st.a, p.list_out, p.counters + 2);
-    }
-};
-struct MstUnite : ElemBase {
-    using Params = MstRoundParams;     // list = the chosen edges, count = their number
-    template <int PH>
-    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
-        const long long i = (long long)bx * THREADS + tid;
-        if (i >= p.count) return;
-        long long map; int e, u, v;
-        mst_edge(p, i, map, e, u, v);
-        const long long o = map * p.H * p.W;
-        // value[u] + 2pi inc[u] continuous with value[v] + 2pi inc[v]:  inc[v] = inc[u] - jump(u, v)
-        const int delta = -jump_between((double)p.w[o + u], (double)p.w[o + v]);
-        if (pot_unite(p.PO + o, u, v, delta)) atomic_add_u32(p.counters, 1u);
-    }
-};
-// path-compress the end points of this round's edges and keep the edges that still cross components
-struct MstCompact : MstListBase {
-    using Params = MstRoundParams;
-    template <int PH>
-    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem, State& st) {
-        if constexpr (PH == 1) {
-            st.a.keep = 0;
-            const long long i = (long long)bx * THREADS + tid;
-            long long map; int e, u, v;
-            if (i < p.count && mst_edge(p, i, map, e, u, v)) {
-                const long long o = map * p.H * p.W;
-                int ru, rv, pu, pv;
-                pot_find(p.PO + o, u, ru, pu);
-                pot_find(p.PO + o, v, rv, pv);
-                if (ru != u) p.PO[o + u] = po_pack(ru, pu);      // one 64-bit store: concurrent walks stay consistent
-                if (rv != v) p.PO[o + v] = po_pack(rv, pv);
-                if (ru != rv) {
-                    st.a.keep = 1;
-                    st.a.value = (unsigned)(map * 2LL * p.H * p.W + e);
-                    // the two components take part in the next round: clear their minima here (same value
-                    // from every thread that touches them)
-                    p.best_w[o + ru] = ~0ull; p.best_e[o + ru] = ~0u;
-                    p.best_w[o + rv] = ~0ull; p.best_e[o + rv] = ~0u;
-                }
-            }
-        }
-        block_append<MstCompact>(PH, tid, smem, st.a, p.list_out, p.counters + 1);
-    }
-};
 struct MstFlatten : ElemBase {
     using Params = MstRoundParams;
     template <int PH>
@@ -371,18 +272,177 @@ struct MstFlatten : ElemBase {
         if (root != px) PO[px] = po_pack(root, pot);     // one 64-bit store: concurrent walks stay consistent
     }
 };
+// After the round-0 forest has been flattened: the first edge list (every edge between two different trees, found by
+// comparing each pixel's root with its right and lower neighbour's), the per-root minima cleared, the roots flagged.
+struct MstBuild : MstListBase {
+    using Params = MstRoundParams;     // count = maps * n pixels
+    struct State { AppendState a; unsigned long long key[2]; unsigned id[2], ru[2], rv[2]; };
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem, State& st) {
+        if constexpr (PH == 1) {
+            st.a.n = 0;
+            const long long i = (long long)bx * THREADS + tid;
+            if (i < p.count) {
+                const int n = p.H * p.W;
+                const long long map = i / n;
+                const long long o = map * n;
+                const int px = (int)(i - o);
+                const int r = px / p.W, c = px - r * p.W;
+                const int rp = po_parent(p.PO[i]);
+                const bool isroot = rp == px;
+                p.isroot0[i] = isroot ? 1 : 0;
+                if (isroot) { p.best_w[i] = ~0ull; p.best_e[i] = ~0u; }
+                const double r0 = p.rel[i];
+                auto consider = [&](bool ok, int q, unsigned e) {
+                    if (!ok) return;
+                    const int rq = po_parent(p.PO[o + q]);
+                    if (rq == rp) return;
+                    const unsigned k = st.a.n++;
+                    st.key[k] = f64_bits(r0 + p.rel[o + q]);
+                    st.id[k] = (unsigned)(map * 2LL * n + e);
+                    st.ru[k] = (unsigned)(o + rp);
+                    st.rv[k] = (unsigned)(o + rq);
+                };
+                consider(c + 1 < p.W, px + 1, (unsigned)px);
+                consider(r + 1 < p.H, px + p.W, (unsigned)(n + px));
+            }
+        }
+        block_append_reserve(PH, tid, smem, st.a, p.counters + 1);
+        if constexpr (PH == 3) {
+            for (unsigned k = 0; k < st.a.n; ++k) {
+                const unsigned at = st.a.slot + k;
+                p.out.key[at] = st.key[k]; p.out.id[at] = st.id[k]; p.out.ru[at] = st.ru[k]; p.out.rv[at] = st.rv[k];
+            }
+        }
+    }
+};
+template <int PASS>   // 0: minimum weight per component, 1: minimum edge id among the minimum-weight edges
+struct MstSelect : ElemBase {
+    using Params = MstRoundParams;
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
+        const long long i = (long long)bx * THREADS + tid;
+        if (i >= (long long)p.counters[3]) return;
+        const unsigned long long key = p.in.key[i];
+        const unsigned ru = p.in.ru[i], rv = p.in.rv[i];
+        if (PASS == 0) {
+            atomic_min_u64(p.best_w + ru, key);
+            atomic_min_u64(p.best_w + rv, key);
+        } else {
+            const unsigned id = p.in.id[i];
+            if (p.best_w[ru] == key) atomic_min_u32(p.best_e + ru, id);
+            if (p.best_w[rv] == key) atomic_min_u32(p.best_e + rv, id);
+        }
+    }
+};
+// edges that some component selected as its minimum
+struct MstMark : MstListBase {
+    using Params = MstRoundParams;
+    struct State { AppendState a; unsigned id; };
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem, State& st) {
+        if constexpr (PH == 1) {
+            st.a.n = 0;
+            const long long i = (long long)bx * THREADS + tid;
+            if (i < (long long)p.counters[3]) {
+                const unsigned id = p.in.id[i];
+                if (p.best_e[p.in.ru[i]] == id || p.best_e[p.in.rv[i]] == id) { st.a.n = 1; st.id = id; }
+            }
+        }
+        block_append_reserve(PH, tid, smem, st.a, p.counters + 2);
+        if constexpr (PH == 3) { if (st.a.n) p.chosen[st.a.slot] = st.id; }
+    }
+};
+struct MstUnite : ElemBase {
+    using Params = MstRoundParams;     // chosen[0 .. counters[2])
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
+        const long long i = (long long)bx * THREADS + tid;
+        if (i >= (long long)p.counters[2]) return;
+        const int n = p.H * p.W;
+        const long long g = (long long)p.chosen[i];
+        const long long map = g / (2LL * n);
+        int u, v;
+        edge_ends((int)(g - map * 2LL * n), n, p.H, p.W, u, v);
+        const long long o = map * n;
+        // value[u] + 2pi inc[u] continuous with value[v] + 2pi inc[v]:  inc[v] = inc[u] - jump(u, v)
+        const int delta = -jump_between((double)p.w[o + u], (double)p.w[o + v]);
+        if (pot_unite(p.PO + o, u, v, delta)) atomic_add_u32(p.counters, 1u);
+    }
+};
+// root of a node that was a root before this round's unions (roots only ever get linked under other roots)
+FCD_HD unsigned root_from(po_t* PO_all, unsigned g, int n) {
+    const unsigned o = (g / (unsigned)n) * (unsigned)n;
+    int root, pot;
+    pot_find_halving(PO_all + o, (int)(g - o), root, pot);
+    return o + (unsigned)root;
+}
+// keep the edges that still cross components, with their roots brought up to date
+struct MstCompact : MstListBase {
+    using Params = MstRoundParams;
+    struct State { AppendState a; unsigned long long key; unsigned id, ru, rv; };
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem, State& st) {
+        if constexpr (PH == 1) {
+            st.a.n = 0;
+            const long long i = (long long)bx * THREADS + tid;
+            if (i < (long long)p.counters[3]) {
+                const int n = p.H * p.W;
+                const unsigned ru = root_from(p.PO, p.in.ru[i], n), rv = root_from(p.PO, p.in.rv[i], n);
+                if (ru != rv) {
+                    st.a.n = 1;
+                    st.key = p.in.key[i]; st.id = p.in.id[i]; st.ru = ru; st.rv = rv;
+                    // the two components take part in the next round: clear their minima here (same value
+                    // from every thread that touches them)
+                    p.best_w[ru] = ~0ull; p.best_e[ru] = ~0u;
+                    p.best_w[rv] = ~0ull; p.best_e[rv] = ~0u;
+                }
+            }
+        }
+        block_append_reserve(PH, tid, smem, st.a, p.counters + 1);
+        if constexpr (PH == 3) {
+            if (st.a.n) {
+                const unsigned at = st.a.slot;
+                p.out.key[at] = st.key; p.out.id[at] = st.id; p.out.ru[at] = st.ru; p.out.rv[at] = st.rv;
+            }
+        }
+    }
+};
+// End of the rounds.  Only the roots of the round-0 forest were ever linked under other nodes; every other pixel
+// still points at such a root (or, after path halving, at another one further up).  Point those roots straight at
+// the root of the whole map ...
+struct MstFlattenRoots : ElemBase {
+    using Params = MstRoundParams;
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
+        const long long i = (long long)bx * THREADS + tid;
+        if (i >= p.count || !p.isroot0[i]) return;
+        const int n = p.H * p.W;
+        po_t* PO = p.PO + (i / n) * n;
+        const int px = (int)(i % n);
+        int root, pot;
+        pot_find(PO, px, root, pot);
+        if (root != px) PO[px] = po_pack(root, pot);
+    }
+};
+// ... so that every pixel is at most two hops from it.
 struct MstApply : ElemBase {
     using Params = MstRoundParams;
+    FCD_HD static int pot_of(const po_t* PO, int px) {
+        const po_t v = PO[px];
+        const int q = po_parent(v);
+        if (q == px) return 0;
+        const po_t v2 = PO[q];
+        return po_off(v) + (po_parent(v2) == q ? 0 : po_off(v2));
+    }
     template <int PH>
     FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
         const long long i = (long long)bx * THREADS + tid;
         if (i >= p.count) return;
         const int n = p.H * p.W;
         const po_t* PO = p.PO + (i / n) * n;
-        int root, pot, root0, pot0;
-        pot_find(PO, (int)(i % n), root, pot);
-        pot_find(PO, 0, root0, pot0);                   // normalisation: pixel (0, 0) keeps its wrapped value
-        p.out[i] = (float)((double)p.w[i] + 2.0 * kPiD * (double)(pot - pot0));
+        // normalisation: pixel (0, 0) keeps its wrapped value
+        p.outp[i] = (float)((double)p.w[i] + 2.0 * kPiD * (double)(pot_of(PO, (int)(i % n)) - pot_of(PO, 0)));
     }
 };
 
