@@ -5,7 +5,7 @@ with the gather of the height maps onto rank 0 running UNDER the computation.
 
 Every rank processes its contiguous frame range (fcd_b200.shard_range) chunk by chunk; there is no collective on
 the hot path.  Timed: (1) frame-sharded compute, no gather; (2) the same with every finished chunk copied into a
-two-slot ring in rank 0's memory by the copy engines (fcd_b200.peer_ring.PeerRing: CUDA IPC memory, one
+ring of slots in rank 0's memory by the copy engines (fcd_b200.peer_ring.PeerRing: symmetric memory, one
 device-to-device copy per chunk over NVLink, control messages over gloo) -- no kernel takes part in the transfer, so
 the persistent FCD grids keep every SM (round 1 streamed the gather with NCCL send/recv, whose copy kernels cost 69 %
 of the throughput).  20k maps are 335 GB and cannot live in one GPU's memory: rank 0 drains each slot as it arrives
@@ -36,51 +36,66 @@ a, b = shard_range(total, rank, ws)
 plan = fcd_b200.HeightMapPlan((n, n), chunk, dev)
 ref, frames = make_frames_gpu(n, chunk, SEED + rank, dev)          # one synthetic chunk per rank, replayed
 plan.bind(ref, square_size=o.board_square_size(n), height=1.0)
-outs = [torch.empty((chunk, n, n), dtype=torch.float32, device=dev) for _ in range(2)]
+NBUF, SLOTS = 3, 4
+outs = [torch.empty((chunk, n, n), dtype=torch.float32, device=dev) for _ in range(NBUF)]
+probe = torch.empty((2, 1024), dtype=torch.float32).pin_memory()
 nchunks_of = [(shard_range(total, r, ws)[1] - shard_range(total, r, ws)[0] + chunk - 1) // chunk for r in range(ws)]
 nchunks = nchunks_of[rank]
 bad = [0]
 
 
-def checksum(t):
-    return int(t.view(torch.int32).to(torch.int64).sum().item())
+def checksum(t, cnt, host):
+    """Checksum of the first and the last 4 KB of chunk t[:cnt], read with two small device-to-host copies (copy
+    engine): no kernel has to find a free SM among the persistent FCD grids."""
+    flat = t[:cnt].reshape(-1)
+    host[0].copy_(flat[:1024], non_blocking=True)
+    host[1].copy_(flat[-1024:], non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    v = host.view(torch.int32).to(torch.int64)
+    return int(v[0].sum()), int(v[1].sum())
+
+
+probe_root = torch.empty((2, 1024), dtype=torch.float32).pin_memory()
 
 
 def consume(src, k, slot, cnt, ck_first, ck_last):
-    if checksum(slot[0]) != ck_first or checksum(slot[cnt - 1]) != ck_last:
+    if checksum(slot, cnt, probe_root) != (ck_first, ck_last):
         bad[0] += 1
 
 
 def run(gather):
-    ring = PeerRing((chunk, n, n), nchunks_of, root=0, slots=2, device=dev, consume=consume) if gather else None
+    ring = PeerRing((chunk, n, n), nchunks_of, root=0, slots=SLOTS, device=dev, consume=consume) if gather else None
     torch.cuda.synchronize(); dist.barrier()
     t0 = time.perf_counter()
-    copied = [None, None]
+    copied = [None] * NBUF
     main = torch.cuda.current_stream()
     for k in range(nchunks):
         cnt = min(chunk, b - a - k * chunk)
-        buf = outs[k & 1]
-        if copied[k & 1] is not None:
-            main.wait_event(copied[k & 1])                 # the copy out of this buffer (chunk k-2) has finished
+        buf = outs[k % NBUF]
+        if copied[k % NBUF] is not None:
+            main.wait_event(copied[k % NBUF])              # the copy out of this buffer (chunk k-NBUF) has finished
         plan.execute(frames[:cnt], out=buf[:cnt], unwrap=mode)
         if gather and rank != 0:
-            copied[k & 1] = ring.push(buf, cnt, tag0=checksum(buf[0]), tag1=checksum(buf[cnt - 1]))
+            c0, c1 = checksum(buf, cnt, probe)
+            copied[k % NBUF] = ring.push(buf, cnt, tag0=c0, tag1=c1)
     torch.cuda.synchronize()
     t_local = time.perf_counter() - t0
+    waits = (0.0, 0.0)
     if ring is not None:
         ring.close()
+        waits = (ring.wait_free_s, ring.wait_copy_s)
     torch.cuda.synchronize(); dist.barrier()
-    return time.perf_counter() - t0, t_local
+    return time.perf_counter() - t0, t_local, waits
 
 
 run(False)
-t_plain, _ = run(False)
-t_gather, t_local = run(True)
+t_plain, _, _ = run(False)
+t_gather, t_local, waits = run(True)
 # small-case check of the chunked NCCL gather used by the library API
 small = plan.execute(frames[:6])
 lo, hi = shard_range(6 * ws, rank, ws)
 full = gather_height_maps(small, 6 * ws, dst=0, chunk_frames=4)
-tl = torch.tensor([t_local], dtype=torch.float64, device=dev)
+tl = torch.tensor([t_local, waits[0], waits[1]], dtype=torch.float64, device=dev)
 dist.all_reduce(tl, op=dist.ReduceOp.MAX)
 if rank == 0:
     ok = bool(torch.equal(full[lo:hi], small)) and full.shape[0] == 6 * ws
@@ -90,9 +105,11 @@ if rank == 0:
                       "frames_per_s_with_streamed_gather": total / t_gather,
                       "streamed_over_no_gather": t_plain / t_gather,
                       "streamed_gather_gbs_into_rank0": remote * n * n * 4 / t_gather / 1e9,
-                      "slowest_rank_compute_s_under_gather": float(tl.item()), "no_gather_s": t_plain,
-                      "gather": "CUDA IPC ring in rank 0's HBM, one device-to-device copy per chunk on the copy engines "
-                                "(cudaMemcpyAsync over NVLink), gloo control messages; no NCCL / no kernels on the data path",
+                      "slowest_rank_compute_s_under_gather": float(tl[0]), "no_gather_s": t_plain,
+                      "sender_wait_for_free_slot_s": float(tl[1]), "sender_wait_for_own_copy_s": float(tl[2]),
+                      "ring_slots": SLOTS, "local_buffers": NBUF,
+                      "gather": "ring in rank 0's HBM mapped through symmetric memory (cuMem), one device-to-device copy per "
+                                "chunk (cudaMemcpyAsync over NVLink), gloo control messages; no NCCL / no kernels on the data path",
                       "chunks_with_bad_checksum": bad[0],
                       "small_gather_bit_exact": ok}))
 dist.destroy_process_group()

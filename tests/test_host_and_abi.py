@@ -101,6 +101,73 @@ def test_sharded_gather_two_ranks_gloo(tmp_path):
     assert "GATHER_OK" in outs[0]
 
 
+_RING_WORKER = r'''
+import os, sys
+import torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "trapped-modes-ltg_b200"))
+from fcd_b200.peer_ring import PeerRing
+rank, world = int(sys.argv[3]), 3
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=rank, world_size=world)
+chunk, nchunks = 5, [0, 9, 7]                      # rank 1 pushes 9 chunks, rank 2 pushes 7 (the last ones ragged)
+seen = {}
+def consume(src, k, slot, cnt, t0, t1):
+    seen[(src, k)] = (cnt, float(slot[:cnt].sum()), t0, t1)
+for slots in (2, 4):
+    seen.clear()
+    ring = PeerRing((chunk, 3, 4), nchunks, root=0, slots=slots, device="cpu", consume=consume)
+    if rank != 0:
+        for k in range(nchunks[rank]):
+            cnt = chunk if k + 1 < nchunks[rank] else 2
+            buf = torch.full((chunk, 3, 4), float(100 * rank + k))
+            ring.push(buf, cnt, tag0=k, tag1=rank)
+    ring.close()
+    if rank == 0:
+        assert len(seen) == 16, seen
+        for (src, k), (cnt, total, t0, t1) in seen.items():
+            assert cnt == (chunk if k + 1 < nchunks[src] else 2) and (t0, t1) == (k, src)
+            assert total == cnt * 12 * (100 * src + k)
+        print("RING_OK", slots)
+dist.barrier(); dist.destroy_process_group()
+'''
+
+
+def test_peer_ring_control_protocol_three_ranks_gloo(tmp_path):
+    """The streamed gather's ring (fcd_b200/peer_ring.py) in its CPU mode: slot-filled / slot-free messages with
+    2 and 4 slots, ragged last chunks, two senders -- the data plane is shared memory here, NVLink on the box."""
+    script = tmp_path / "ring_worker.py"
+    script.write_text(_RING_WORKER)
+    port = str(31500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(3)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "RING_OK 2" in outs[0] and "RING_OK 4" in outs[0]
+
+
+def test_load_image_gray_and_colour(tmp_path):
+    """analyze.load_image (pydata/analyze.py:26-40: skimage.io.imread(as_gray=True).astype(float32)): 2-D files keep
+    their values, colour files take scikit-image's luminance (restated; scikit-image is not installed here)."""
+    import cv2
+    from pydata.analyze import analyze
+    rng = np.random.default_rng(1)
+    g16 = rng.integers(0, 1024, (12, 9), dtype=np.uint16)
+    cv2.imwrite(str(tmp_path / "g.tif"), g16)
+    out = analyze.load_image(str(tmp_path / "g.tif"))
+    assert out.dtype == np.float32 and np.array_equal(out, g16.astype(np.float32))
+    rgb = rng.integers(0, 256, (7, 5, 3), dtype=np.uint8)                      # R, G, B
+    cv2.imwrite(str(tmp_path / "c.png"), rgb[..., ::-1])                       # OpenCV writes B, G, R
+    want = (rgb.astype(np.float64) / 255.0) @ np.array([0.2125, 0.7154, 0.0721])
+    got = analyze.load_image(str(tmp_path / "c.png"))
+    assert got.dtype == np.float32 and np.allclose(got, want, rtol=0, atol=1e-7)
+    rgba = np.concatenate([rgb, rng.integers(0, 256, (7, 5, 1), dtype=np.uint8)], axis=2)
+    cv2.imwrite(str(tmp_path / "a.png"), rgba[..., [2, 1, 0, 3]])
+    a = rgba[..., 3:4] / 255.0
+    want = ((1 - a) + a * rgba[..., :3] / 255.0) @ np.array([0.2125, 0.7154, 0.0721])
+    assert np.allclose(analyze.load_image(str(tmp_path / "a.png")), want, rtol=0, atol=1e-7)
+    with pytest.raises(FileNotFoundError):
+        analyze.load_image(str(tmp_path / "missing.tif"))
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` runs on CPU: exactly one JSON line on stdout with the contract keys."""
     import json

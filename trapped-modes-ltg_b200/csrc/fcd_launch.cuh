@@ -120,6 +120,10 @@ inline void h2d(void* d, const void* h, size_t n, stream_t s) {
     check(cudaStreamSynchronize((cudaStream_t)s), "sync after h2d");
 }
 inline void d2h(void* h, const void* d, size_t n, stream_t s) {
+    // Wait for the stream FIRST: a copy into pageable memory that has to wait for queued kernels does so inside the
+    // driver, where it blocks the CUDA calls of every other thread of the process (a consumer thread draining a gather
+    // ring lost a whole wave per chunk to this); after the wait the copy itself is immediate.
+    check(cudaStreamSynchronize((cudaStream_t)s), "sync before d2h");
     check(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, (cudaStream_t)s), "cudaMemcpyAsync d2h");
     check(cudaStreamSynchronize((cudaStream_t)s), "sync after d2h");
 }

@@ -566,7 +566,7 @@ struct PlanImpl {
     rt::DevBuf<double> u_rel, u_border;
     rt::DevBuf<po_t> u_po;
     rt::DevBuf<unsigned long long> u_bw, u_key[2];
-    rt::DevBuf<unsigned> u_be, u_counters, u_id[2], u_ru[2], u_rv[2], u_chosen;
+    rt::DevBuf<unsigned> u_be, u_counters, u_id[2], u_ru[2], u_rv[2];
     rt::DevBuf<unsigned char> u_isroot;
     long long unwrap_rounds = 0;
 
@@ -589,7 +589,6 @@ struct PlanImpl {
         const int wave = unwrap_wave_maps();
         const size_t cap = (size_t)wave * n;
         u_rel.grow(cap); u_po.grow(cap); u_bw.grow(cap); u_be.grow(cap); u_isroot.grow(cap); u_counters.grow(4);
-        u_chosen.grow(cap);                                   // at most one chosen edge per component
         for (int k = 0; k < 2; ++k) {                         // a map has fewer than 2n edges
             u_key[k].grow(2 * cap); u_id[k].grow(2 * cap); u_ru[k].grow(2 * cap); u_rv[k].grow(2 * cap);
         }
@@ -598,7 +597,7 @@ struct PlanImpl {
             const long long total = nm * n;
             const float* w = wrapped + m0 * n;
             launch<MstReliability>(blocks_for(total), 1, s, MstRelParams{w, u_border.ptr, u_rel.ptr, u_po.ptr, total, H, W});
-            MstRoundParams base{w, u_rel.ptr, u_po.ptr, u_bw.ptr, u_be.ptr, EdgeList{}, EdgeList{}, u_chosen.ptr,
+            MstRoundParams base{w, u_rel.ptr, u_po.ptr, u_bw.ptr, u_be.ptr, EdgeList{}, EdgeList{},
                                 u_counters.ptr, u_isroot.ptr, total, H, W, nullptr};
             auto list_of = [&](int k) { return EdgeList{u_key[k].ptr, u_id[k].ptr, u_ru[k].ptr, u_rv[k].ptr}; };
             // round 0: every pixel is a component (local minima, no unions), then the first list of cross edges
@@ -621,12 +620,11 @@ struct PlanImpl {
                 rp.in = list_of(cur); rp.out = list_of(cur ^ 1); rp.count = count;
                 launch<MstSelect<0>>(blocks_for(count), 1, s, rp);
                 launch<MstSelect<1>>(blocks_for(count), 1, s, rp);
-                launch<MstMark>(blocks_for(count), 1, s, rp);
-                launch<MstUnite>(blocks_for(std::min<long long>(count, total)), 1, s, rp);   // chosen <= components
+                launch<MstHook>(blocks_for(count), 1, s, rp);
                 launch<MstCompact>(blocks_for(count), 1, s, rp);
                 rt::d2h(c, u_counters.ptr, sizeof(c), s);
                 ++unwrap_rounds;
-                if (c[2] == 0 && c[1] != 0) rt::fail("unwrap: cross edges left but none selected");
+                if ((long long)c[1] >= count) rt::fail("unwrap: a round merged nothing");
                 count = c[1];
                 cur ^= 1;
             }

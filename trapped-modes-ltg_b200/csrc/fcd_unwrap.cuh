@@ -101,27 +101,6 @@ FCD_HD void pot_find_halving(po_t* PO, int x, int& root, int& pot) {
         }
     }
 }
-// make pot(v) = pot(u) + delta by linking the two roots (larger index under smaller)
-FCD_HD bool pot_unite(po_t* PO, int u, int v, int delta) {
-    for (;;) {
-        int ru, pu, rv, pv;
-        pot_find_halving(PO, u, ru, pu);
-        pot_find_halving(PO, v, rv, pv);
-        if (ru == rv) return false;
-        int child, parent, off;
-        if (ru < rv) { child = rv; parent = ru; off = pu + delta - pv; }
-        else         { child = ru; parent = rv; off = pv - delta - pu; }
-        const po_t expected = po_pack(child, 0), desired = po_pack(parent, off);
-#if defined(__CUDA_ARCH__)
-        const po_t old = atomicCAS(PO + child, expected, desired);
-#else
-        const po_t old = PO[child];
-        if (old == expected) PO[child] = desired;
-#endif
-        if (old == expected) return true;
-    }
-}
-
 // edge e of a map with n = H*W pixels: e < n horizontal (p, p+1), e >= n vertical (p, p+W)
 FCD_HD bool edge_ends(int e, int n, int H, int W, int& p, int& q) {
     if (e < n) { p = e; q = e + 1; return (e % W) != W - 1; }
@@ -187,8 +166,7 @@ struct MstRoundParams {
     unsigned long long* best_w;   // [maps][n] per root: smallest outgoing weight
     unsigned* best_e;             // [maps][n] per root: smallest edge id among those of that weight
     EdgeList in, out;             // this round's list / the list being written (MstBuild, MstCompact)
-    unsigned* chosen;             // MstMark -> MstUnite: ids of the edges some component selected
-    unsigned* counters;           // [0] merges, [1] length of `out`, [2] length of `chosen`, [3] length of `in`
+    unsigned* counters;           // [1] length of `out`, [3] length of `in`
     unsigned char* isroot0;       // [maps][n] 1 for the roots of the round-0 forest (the only nodes later unions move)
     long long count;              // upper bound of the items of this launch (the exact list lengths are counters)
     int H, W;
@@ -252,7 +230,7 @@ struct MstRound0 : ElemBase {
         if (q < 0) return;                                            // a 1 x 1 map: stays its own root
         best_edge(rel, q, p.H, p.W, bq, qq);
         if (bq == be && px < q) return;                               // mutual pick: the smaller pixel is the root
-        // pot(v) = pot(u) - jump(u, v) for the edge (u, v), u < v   (same convention as MstUnite)
+        // pot(v) = pot(u) - jump(u, v) for the edge (u, v), u < v   (same convention as MstHook)
         const float* w = p.w + o;
         const int off = q < px ? -jump_between((double)w[q], (double)w[px]) : jump_between((double)w[px], (double)w[q]);
         p.PO[o + px] = po_pack(q, off);
@@ -335,39 +313,43 @@ struct MstSelect : ElemBase {
         }
     }
 };
-// edges that some component selected as its minimum
-struct MstMark : MstListBase {
-    using Params = MstRoundParams;
-    struct State { AppendState a; unsigned id; };
-    template <int PH>
-    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem, State& st) {
-        if constexpr (PH == 1) {
-            st.a.n = 0;
-            const long long i = (long long)bx * THREADS + tid;
-            if (i < (long long)p.counters[3]) {
-                const unsigned id = p.in.id[i];
-                if (p.best_e[p.in.ru[i]] == id || p.best_e[p.in.rv[i]] == id) { st.a.n = 1; st.id = id; }
-            }
-        }
-        block_append_reserve(PH, tid, smem, st.a, p.counters + 2);
-        if constexpr (PH == 3) { if (st.a.n) p.chosen[st.a.slot] = st.id; }
+// Hooking.  Every component selected exactly one edge, and that edge sits in exactly one list entry, so the entry
+// that carries a component's pick links that component's root under the root at the other end by writing the root's
+// OWN union-find word: one writer per word, no compare-and-swap, no retry.  The picks form a forest once every
+// mutual pick (the only cycle a strict order allows) keeps its smaller root, so roots may hook under roots that
+// hook elsewhere in the same launch.  Potentials of the end points are taken relative to the roots the entry
+// caches -- the walk stops there, because the word above may already have been rewritten by its owner.
+FCD_HD int pot_until(const po_t* PO, int x, int root) {
+    int acc = 0;
+    while (x != root) {
+        const po_t v = po_load(PO + x);
+        acc += po_off(v);
+        x = po_parent(v);
     }
-};
-struct MstUnite : ElemBase {
-    using Params = MstRoundParams;     // chosen[0 .. counters[2])
+    return acc;
+}
+struct MstHook : ElemBase {
+    using Params = MstRoundParams;
     template <int PH>
     FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
         const long long i = (long long)bx * THREADS + tid;
-        if (i >= (long long)p.counters[2]) return;
+        if (i >= (long long)p.counters[3]) return;
+        const unsigned id = p.in.id[i], gu = p.in.ru[i], gv = p.in.rv[i];
+        const bool cu = p.best_e[gu] == id, cv = p.best_e[gv] == id;
+        if (!cu && !cv) return;
         const int n = p.H * p.W;
-        const long long g = (long long)p.chosen[i];
-        const long long map = g / (2LL * n);
+        const long long map = (long long)id / (2LL * n);
         int u, v;
-        edge_ends((int)(g - map * 2LL * n), n, p.H, p.W, u, v);
+        edge_ends((int)((long long)id - map * 2LL * n), n, p.H, p.W, u, v);
         const long long o = map * n;
+        po_t* PO = p.PO + o;
+        const int ru = (int)((long long)gu - o), rv = (int)((long long)gv - o);
         // value[u] + 2pi inc[u] continuous with value[v] + 2pi inc[v]:  inc[v] = inc[u] - jump(u, v)
         const int delta = -jump_between((double)p.w[o + u], (double)p.w[o + v]);
-        if (pot_unite(p.PO + o, u, v, delta)) atomic_add_u32(p.counters, 1u);
+        const int pu = pot_until(PO, u, ru), pv = pot_until(PO, v, rv);
+        const bool v_under_u = (cu && cv) ? (ru < rv) : cv;
+        if (v_under_u) po_store(PO + rv, po_pack(ru, pu + delta - pv));
+        else po_store(PO + ru, po_pack(rv, pv - delta - pu));
     }
 };
 // root of a node that was a root before this round's unions (roots only ever get linked under other roots)

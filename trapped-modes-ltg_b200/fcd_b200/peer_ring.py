@@ -16,10 +16,17 @@ memory and the root therefore drains ring slots as they arrive.
 from __future__ import annotations
 
 import threading
+import time
 from typing import Callable, Optional
 
 import torch
 import torch.distributed as dist
+
+
+class _NoEvent:
+    """Stand-in for torch.cuda.Event in the CPU (test) mode: copies are synchronous."""
+    def synchronize(self) -> None:
+        pass
 
 
 class PeerRing:
@@ -32,31 +39,47 @@ class PeerRing:
 
     def __init__(self, chunk_shape, chunks_per_rank, root: int = 0, slots: int = 2, device=None,
                  consume: Optional[Callable] = None, dtype=torch.float32):
-        import torch.distributed._symmetric_memory as symm_mem
-
         self.rank, self.world, self.root, self.slots = dist.get_rank(), dist.get_world_size(), root, slots
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.cpu = self.device.type == "cpu"                    # CPU mode (tests): ring in POSIX shared memory
         self.chunks_per_rank = list(chunks_per_rank)            # number of chunks every rank will push
         self.ctrl = dist.new_group(backend="gloo")              # control plane: CPU tensors, no GPU kernels
-        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.copy_stream = None if self.cpu else torch.cuda.Stream(device=self.device)
         self._k = 0
         self._copied = [None] * slots                           # events: copy out of the local buffer finished
         self._thread = None
         self.consumed = 0
-        # symmetric allocation: every rank allocates the ring, only the root's copy is used
+        self.wait_free_s = 0.0       # sender: time blocked on "slot free" messages
+        self.wait_copy_s = 0.0       # sender: time blocked on its own copies before announcing them
         shape = (self.world, slots) + tuple(chunk_shape)
-        self._symm = symm_mem.empty(shape, dtype=dtype, device=self.device)
-        self._hdl = symm_mem.rendezvous(self._symm, dist.group.WORLD)
+        if self.cpu:
+            import math
+            import os
+            import uuid
+            path = [f"/dev/shm/fcd_ring_{os.getpid()}_{uuid.uuid4().hex}" if self.rank == root else None]
+            dist.broadcast_object_list(path, src=root, group=self.ctrl)
+            self._shm_path = path[0]
+            numel = math.prod(shape)
+            if self.rank == root:
+                self._symm = torch.from_file(self._shm_path, shared=True, size=numel, dtype=dtype).view(shape)
+            dist.barrier(group=self.ctrl)
+            peer = self._symm if self.rank == root else \
+                torch.from_file(self._shm_path, shared=True, size=numel, dtype=dtype).view(shape)
+        else:
+            import torch.distributed._symmetric_memory as symm_mem
+            # symmetric allocation: every rank allocates the ring, only the root's copy is used
+            self._symm = symm_mem.empty(shape, dtype=dtype, device=self.device)
+            self._hdl = symm_mem.rendezvous(self._symm, dist.group.WORLD)
+            peer = self._symm if self.rank == root else self._hdl.get_buffer(root, shape, dtype)
         if self.rank != root:
-            peer = self._hdl.get_buffer(root, shape, dtype)     # the root's ring, mapped into this process
-            self.views = [peer[self.rank, slot] for slot in range(slots)]
+            self.views = [peer[self.rank, slot] for slot in range(slots)]       # the root's ring, mapped into this process
         else:
             self.ring = {src: [self._symm[src, slot] for slot in range(slots)]
                          for src in range(self.world) if src != root}
             self._consume = consume
             self._thread = threading.Thread(target=self._serve, daemon=True)
             self._thread.start()
-        dist.barrier()
+        dist.barrier(group=self.ctrl)
 
     # ------------------------------------------------------------------ senders
     def push(self, chunk: torch.Tensor, n_frames: int, ready: Optional[torch.cuda.Event] = None, tag0: int = 0,
@@ -68,15 +91,21 @@ class PeerRing:
         k, slot = self._k, self._k % self.slots
         if k >= self.slots:                                     # wait until the root has drained this slot
             free = torch.zeros(1, dtype=torch.int64)
+            t0 = time.perf_counter()
             dist.recv(free, src=self.root, group=self.ctrl, tag=slot)
-        if ready is None:
-            ready = torch.cuda.Event()
-            ready.record(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(self.copy_stream):
-            self.copy_stream.wait_event(ready)
-            self.views[slot][:n_frames].copy_(chunk[:n_frames], non_blocking=True)     # peer copy, copy engine
-            done = torch.cuda.Event()
-            done.record(self.copy_stream)
+            self.wait_free_s += time.perf_counter() - t0
+        if self.cpu:
+            self.views[slot][:n_frames].copy_(chunk[:n_frames])
+            done = _NoEvent()
+        else:
+            if ready is None:
+                ready = torch.cuda.Event()
+                ready.record(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(ready)
+                self.views[slot][:n_frames].copy_(chunk[:n_frames], non_blocking=True)     # peer copy, copy engine
+                done = torch.cuda.Event()
+                done.record(self.copy_stream)
         self._copied[slot] = (done, k, n_frames, int(tag0), int(tag1))
         self._k += 1
         # announce the previous chunk once its copy has landed (its wait overlaps the kernels queued meanwhile)
@@ -88,19 +117,36 @@ class PeerRing:
             item = self._copied[slot]
             if item is not None and item[1] <= upto:
                 done, k, n_frames, t0, t1 = item
+                tw = time.perf_counter()
                 done.synchronize()
-                dist.send(torch.tensor([k, n_frames, t0, t1], dtype=torch.int64), dst=self.root, group=self.ctrl,
-                          tag=self.slots + slot)
+                self.wait_copy_s += time.perf_counter() - tw
+                self._post(torch.tensor([k, n_frames, t0, t1], dtype=torch.int64), self.root, self.slots + slot)
                 self._copied[slot] = None
+
+    def _post(self, msg: torch.Tensor, dst: int, tag: int) -> None:
+        """Non-blocking control message.  gloo's send is a rendezvous with the matching recv; a blocking send from
+        the root ("slot free") and one from a sender ("slot filled") can wait for each other as soon as the ring
+        has more than two slots, so both directions post and move on."""
+        self._posted = [(w, m) for w, m in getattr(self, "_posted", []) if not w.is_completed()]
+        self._posted.append((dist.isend(msg, dst=dst, group=self.ctrl, tag=tag), msg))
+
+    def _drain_posts(self) -> None:
+        for w, _ in getattr(self, "_posted", []):
+            w.wait()
+        self._posted = []
 
     def flush(self) -> None:
         if self.rank != self.root:
             self._announce(upto=self._k)
+        self._drain_posts()
 
     # ------------------------------------------------------------------ root
     def _serve(self) -> None:
-        torch.cuda.set_device(self.device)
-        stream = torch.cuda.Stream(device=self.device)
+        import contextlib
+        stream = None
+        if not self.cpu:
+            torch.cuda.set_device(self.device)
+            stream = torch.cuda.Stream(device=self.device, priority=-1)
         pending = {src: 0 for src in self.ring}
         msg = torch.zeros(4, dtype=torch.int64)
         while any(pending[src] < self.chunks_per_rank[src] for src in pending):
@@ -112,20 +158,27 @@ class PeerRing:
                 dist.recv(msg, src=src, group=self.ctrl, tag=self.slots + slot)
                 n_frames = int(msg[1])
                 if self._consume is not None:
-                    with torch.cuda.stream(stream):
+                    with (contextlib.nullcontext() if stream is None else torch.cuda.stream(stream)):
                         self._consume(src, k, self.ring[src][slot], n_frames, int(msg[2]), int(msg[3]))
-                    stream.synchronize()
+                    if stream is not None:
+                        stream.synchronize()
                 self.consumed += n_frames
                 pending[src] = k + 1
                 if k + self.slots < self.chunks_per_rank[src]:
-                    dist.send(torch.ones(1, dtype=torch.int64), dst=src, group=self.ctrl, tag=slot)
+                    self._post(torch.ones(1, dtype=torch.int64), src, slot)
 
     def close(self) -> None:
         self.flush()
         if self._thread is not None:
             self._thread.join()
-        torch.cuda.synchronize(self.device)
-        dist.barrier()
+            self._drain_posts()
+        if not self.cpu:
+            torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.ctrl)
         if self.rank != self.root:
             del self.views
-        dist.barrier()
+        dist.barrier(group=self.ctrl)
+        if self.cpu and self.rank == self.root:
+            import os
+            del self.ring, self._symm
+            os.unlink(self._shm_path)

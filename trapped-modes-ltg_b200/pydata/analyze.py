@@ -44,13 +44,27 @@ class analyze:
     @classmethod
     def load_image(cls, path):
         """Grayscale image as float32.  Reference: pydata/analyze.py:26-40 (skimage.io.imread(as_gray=True)).
-        Host-side file decode (OpenCV); single-channel files are returned unchanged in value."""
+        Host-side file decode (OpenCV).  Single-channel files are returned unchanged in value (what as_gray does to
+        a 2-D image: nothing).  Colour files go through scikit-image's documented conversion, restated here because
+        scikit-image is not installed (unpinned, like the other scikit-image boundaries): integers scaled to [0, 1]
+        (img_as_float), RGBA blended over white (rgba2rgb), luminance 0.2125 R + 0.7154 G + 0.0721 B (rgb2gray)."""
         import cv2
         img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
         if img is None:
             raise FileNotFoundError(path)
         if img.ndim == 3:
-            raise ValueError("colour images are not supported by this mirror (the reference fixtures are grayscale)")
+            if img.dtype == np.uint8:
+                f = img.astype(np.float64) / 255.0
+            elif img.dtype == np.uint16:
+                f = img.astype(np.float64) / 65535.0
+            else:
+                f = img.astype(np.float64)
+            if f.shape[2] == 4:                                   # OpenCV order B, G, R, A
+                a = f[..., 3:4]
+                f = np.clip((1.0 - a) + a * f[..., :3], 0.0, 1.0)
+            elif f.shape[2] != 3:
+                raise ValueError(f"unsupported channel count {f.shape[2]}")
+            return (0.2125 * f[..., 2] + 0.7154 * f[..., 1] + 0.0721 * f[..., 0]).astype(np.float32)
         return img.astype(np.float32)
 
     @classmethod
