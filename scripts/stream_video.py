@@ -36,7 +36,15 @@ a, b = shard_range(total, rank, ws)
 plan = fcd_b200.HeightMapPlan((n, n), chunk, dev)
 ref, frames = make_frames_gpu(n, chunk, SEED + rank, dev)          # one synthetic chunk per rank, replayed
 plan.bind(ref, square_size=o.board_square_size(n), height=1.0)
-NBUF, SLOTS = 3, 4
+NBUF, SLOTS = 3, int(os.environ.get("FCD_RING_SLOTS", "4"))
+T0 = time.time()
+
+
+def note(msg):
+    if rank in (0, ws - 1) and os.environ.get("FCD_STREAM_VERBOSE"):
+        print(f"[{time.time() - T0:7.2f}s rank {rank}] {msg}", file=sys.stderr, flush=True)
+
+
 outs = [torch.empty((chunk, n, n), dtype=torch.float32, device=dev) for _ in range(NBUF)]
 probe = torch.empty((2, 1024), dtype=torch.float32).pin_memory()
 nchunks_of = [(shard_range(total, r, ws)[1] - shard_range(total, r, ws)[0] + chunk - 1) // chunk for r in range(ws)]
@@ -64,7 +72,9 @@ def consume(src, k, slot, cnt, ck_first, ck_last):
 
 
 def run(gather):
+    note(f"run(gather={gather}): building ring" if gather else "run(gather=False)")
     ring = PeerRing((chunk, n, n), nchunks_of, root=0, slots=SLOTS, device=dev, consume=consume) if gather else None
+    note("ring ready")
     torch.cuda.synchronize(); dist.barrier()
     t0 = time.perf_counter()
     copied = [None] * NBUF
@@ -78,7 +88,10 @@ def run(gather):
         if gather and rank != 0:
             c0, c1 = checksum(buf, cnt, probe)
             copied[k % NBUF] = ring.push(buf, cnt, tag0=c0, tag1=c1)
+        if k % 8 == 0:
+            note(f"chunk {k} / {nchunks} queued")
     torch.cuda.synchronize()
+    note("local compute done")
     t_local = time.perf_counter() - t0
     waits = (0.0, 0.0)
     if ring is not None:

@@ -108,7 +108,8 @@ sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "t
 from fcd_b200.peer_ring import PeerRing
 rank, world = int(sys.argv[3]), 3
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=rank, world_size=world)
-chunk, nchunks = 5, [0, 9, 7]                      # rank 1 pushes 9 chunks, rank 2 pushes 7 (the last ones ragged)
+import time
+chunk, nchunks = 5, [0, 90, 70]                    # rank 1 pushes 90 chunks, rank 2 pushes 70 (the last ones ragged)
 seen = {}
 def consume(src, k, slot, cnt, t0, t1):
     seen[(src, k)] = (cnt, float(slot[:cnt].sum()), t0, t1)
@@ -119,10 +120,13 @@ for slots in (2, 4):
         for k in range(nchunks[rank]):
             cnt = chunk if k + 1 < nchunks[rank] else 2
             buf = torch.full((chunk, 3, 4), float(100 * rank + k))
+            time.sleep(0.002)
             ring.push(buf, cnt, tag0=k, tag1=rank)
+    else:
+        time.sleep(0.1)        # the root finishes its own work mid-stream and closes while its consumer is still busy
     ring.close()
     if rank == 0:
-        assert len(seen) == 16, seen
+        assert len(seen) == 160, len(seen)
         for (src, k), (cnt, total, t0, t1) in seen.items():
             assert cnt == (chunk if k + 1 < nchunks[src] else 2) and (t0, t1) == (k, src)
             assert total == cnt * 12 * (100 * src + k)
@@ -133,7 +137,8 @@ dist.barrier(); dist.destroy_process_group()
 
 def test_peer_ring_control_protocol_three_ranks_gloo(tmp_path):
     """The streamed gather's ring (fcd_b200/peer_ring.py) in its CPU mode: slot-filled / slot-free messages with
-    2 and 4 slots, ragged last chunks, two senders -- the data plane is shared memory here, NVLink on the box."""
+    2 and 4 slots, ragged last chunks, two senders, the root closing mid-stream (a hang on 8 GPUs came from exactly
+    that) -- the data plane is shared memory here, NVLink on the box."""
     script = tmp_path / "ring_worker.py"
     script.write_text(_RING_WORKER)
     port = str(31500 + os.getpid() % 2000)

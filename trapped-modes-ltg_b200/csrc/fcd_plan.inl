@@ -404,18 +404,23 @@ struct PlanImpl {
             launch<ColBand<L, G>>(ceil_div(ncp, G), a.nf * 2, s, p);
         })
         if (profiling) timer.mark(s, 1);
+        stage_demod(0, a.nf, po, scan, flags, s);
+    }
+    // K3 alone on the band-passed spectra w2 of frames [wf, wf + nf) of the current wave; writes w3 / colphase from
+    // frame 0 on (the second look of unwrap "auto" demodulates a run of flagged frames again without redoing K1, K2)
+    void stage_demod(int wf, int nf, float* po, int scan, int* flags, rt::stream_t s) {
         FCD_DISPATCH_L(W, {
             constexpr int G = Tune<L>::GDEM;
-            RowDemodParams p{w2.ptr, theta.ptr, w3.ptr, colphase.ptr, po, tw_w_f.ptr, H, ncp,
+            RowDemodParams p{w2.ptr + (size_t)wf * 2 * H * ncp, theta.ptr, w3.ptr, colphase.ptr, po, tw_w_f.ptr, H, ncp,
                              {nc[0], nc[1]}, {c_lo[0] - W / 2, c_lo[1] - W / 2}, W / 2, scan, flags};
             bool pruned = false;
             if constexpr (Plan<L>::R1 == 8) {
                 if (nc[0] <= L / 8 && nc[1] <= L / 8) {
                     pruned = true;
-                    launch<RowDemod<L, G, true>>(a.nf, H / G, s, p);
+                    launch<RowDemod<L, G, true>>(nf, H / G, s, p);
                 }
             }
-            if (!pruned) launch<RowDemod<L, G, false>>(a.nf, H / G, s, p);
+            if (!pruned) launch<RowDemod<L, G, false>>(nf, H / G, s, p);
         })
         if (profiling) timer.mark(s, 2);
     }
@@ -473,7 +478,7 @@ struct PlanImpl {
     static constexpr int kProbe = 16;         // frames per residue probe (bounds the phase scratch)
 
     // Frames [w0, w0 + a.nf) of the call: after the scan pass, look again at the frames K3 flagged.  Their wrapped
-    // phases are materialised (K1-K3 once more, into scratch), residues counted, and only frames that hold any
+    // phases are materialised (K3 once more on the wave's band-passed spectra, into scratch), residues counted, and only frames that hold any
     // are unwrapped along the reliability-guided tree and re-integrated -- bit for bit what unwrap = 2 does.
     // A frame without residues keeps its scan result: there every unwrapper gives the same integers.
     void auto_second_look(const Wave& a, int w0, float* po_user, rt::stream_t s) {
@@ -490,7 +495,7 @@ struct PlanImpl {
             ph_ws.grow((size_t)kProbe * 2 * n);
             if (profiling) timer.begin_chunk(s, m);
             const Wave sub = sub_wave(a, i, m, n);
-            stage_front(sub, ph_ws.ptr, 0, nullptr, s);           // wrapped phases of the run -> scratch
+            stage_demod(i, m, ph_ws.ptr, 0, nullptr, s);          // wrapped phases of the run -> scratch (w2 is still the wave's)
             res_counts.grow((size_t)2 * kProbe);
             rt::dmemset(res_counts.ptr, 0, sizeof(int) * 2 * kProbe, s);
             launch<ResidueCount>(H - 1, 2 * m, s, ResidueParams{ph_ws.ptr, res_counts.ptr, H, W});

@@ -31,7 +31,8 @@ class _NoEvent:
 
 class PeerRing:
     """root: owns `slots` buffers of `chunk` maps per source rank (symmetric allocation: (world * slots) chunks on
-    every rank, only the root's are written) and a consumer thread that calls
+    every rank, only the root's are written -- size the chunk accordingly: 8 ranks x 4 slots x 128 maps of 2048^2 are
+    69 GB per GPU) and a consumer thread that calls
     `consume(src, chunk_index, slot_tensor, n_frames, tag0, tag1)` for every filled slot, then frees it.
     other ranks: `push(local_chunk_tensor, n_frames)` copies a finished chunk into the next slot on a side stream.
 
@@ -136,9 +137,10 @@ class PeerRing:
         self._posted = []
 
     def flush(self) -> None:
+        """Sender: announce every chunk pushed so far and wait until the root has taken the messages."""
         if self.rank != self.root:
             self._announce(upto=self._k)
-        self._drain_posts()
+            self._drain_posts()
 
     # ------------------------------------------------------------------ root
     def _serve(self) -> None:
@@ -168,6 +170,9 @@ class PeerRing:
                     self._post(torch.ones(1, dtype=torch.int64), src, slot)
 
     def close(self) -> None:
+        # The list of posted messages belongs to ONE thread at a time: on the root that is the consumer thread until
+        # it has been joined (draining it from here while the consumer still posts dropped in-flight "slot free"
+        # messages, and the senders waited for them forever).
         self.flush()
         if self._thread is not None:
             self._thread.join()
