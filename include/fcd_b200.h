@@ -9,7 +9,11 @@
  * No torch types, no exceptions: every function returns 0 on success or a negative code,
  * and fcd_last_error() returns the message of the last failure on the calling thread.
  * A plan is bound to one device and may be used from one stream at a time.
- * Supported shapes: rows and cols powers of two in [64, 4096].
+ * Shapes: rows and cols powers of two in [64, 4096] give a FUSED plan (the float32 pipeline, fcd_execute, the
+ * structure mask).  Any other shape with 2 <= rows, cols <= 2048 gives a GENERIC plan: the reference takes any shape
+ * (pyfcd/fcd.py:14), and for those the float64 stage-level entry points (carrier search, bind, carrier mask / ccsgn,
+ * fcd_fft2_c128 -- through Bluestein's chirp convolution on padded power-of-two transforms --, fcd_unwrap_phase,
+ * fcd_count_residues) work and the host layer composes the per-frame path from them.
  */
 #ifndef FCD_B200_H
 #define FCD_B200_H
@@ -184,6 +188,8 @@ int fcd_stage_times(fcd_plan* plan, double ms_out[7], long long launches_out[7],
  * padded number of band columns per carrier (workspace geometry). */
 long long fcd_launch_count(const fcd_plan* plan);
 int fcd_band_columns(const fcd_plan* plan);
+/* 1 for a fused plan (power-of-two shape: fcd_execute available), 0 for a generic one. */
+int fcd_plan_is_fused(const fcd_plan* plan);
 
 #ifdef __cplusplus
 }

@@ -164,9 +164,15 @@ def test_error_behaviour():
     l = lib()
     import ctypes
     h = ctypes.c_void_p()
-    assert l.fcd_plan_create(100, 256, 1, ctypes.byref(h)) == _native.FCD_ERR_INVALID      # not a power of two
+    assert l.fcd_plan_create(100, 256, 1, ctypes.byref(h)) == _native.FCD_OK               # not a power of two: a generic plan
+    assert l.fcd_plan_is_fused(h) == 0
+    f = np.zeros((1, 100, 256), np.float32)
+    assert l.fcd_execute(h, f.ctypes.data, 1, f.ctypes.data, None, None, 0, 1, None) == _native.FCD_ERR_INVALID
+    assert b"powers of two" in l.fcd_last_error()                                            # the fused pipeline is not for it
+    assert l.fcd_plan_destroy(h) == _native.FCD_OK
+    assert l.fcd_plan_create(256, 8192, 1, ctypes.byref(h)) == _native.FCD_ERR_INVALID       # beyond the largest plan
+    assert l.fcd_plan_create(3000, 100, 1, ctypes.byref(h)) == _native.FCD_ERR_INVALID       # generic plans stop at 2048
     assert b"powers of two" in l.fcd_last_error()
-    assert l.fcd_plan_create(256, 8192, 1, ctypes.byref(h)) == _native.FCD_ERR_INVALID
     plan = EmulPlan((64, 64))
     f = np.zeros((1, 64, 64), np.float32)
     rc = l.fcd_execute(plan.h, f.ctypes.data, 1, f.ctypes.data, None, None, 0, 1, None)
@@ -255,4 +261,50 @@ def test_empty_batches_and_bad_modes():
     for mode in (0, 1, 2, 3):
         h = plan.execute(ref.astype(np.float32), unwrap=mode)
         assert np.abs(h).max() < 1e-4
+    plan.close()
+
+
+# ----------------------------------------------------------------------------- shapes that are not powers of two
+@pytest.mark.parametrize("shape", [(60, 100), (75, 64), (64, 96), (33, 47)])
+def test_generic_plan_fft2_any_shape(shape):
+    """A plan of any shape is GENERIC: fcd_fft2_c128 runs Bluestein's chirp convolution on padded power-of-two
+    transforms and must equal scipy's fft2 / ifft2 (the reference calls them on whatever shape it is given)."""
+    import scipy.fft as sfft
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+    plan = EmulPlan(shape)
+    f = plan.fft2(x)
+    assert np.abs(f - sfft.fft2(x)).max() < 1e-11 * np.abs(f).max()
+    assert np.abs(plan.fft2(f, inverse=True) - x).max() < 1e-12
+    with pytest.raises(_native.FcdError) as e:                      # the fused pipeline needs powers of two
+        plan.execute(np.zeros((1,) + shape, np.float32))
+    assert e.value.code in (_native.FCD_ERR_INVALID, _native.FCD_ERR_STATE)
+    plan.close()
+
+
+def test_generic_plan_carriers_match_oracle():
+    """Carrier search, disk masks and ccsgn on a 120 x 150 board (odd half sizes exercise the fftshift bookkeeping)."""
+    from fcd_b200 import synthetic as syn
+    n0, n1 = 120, 150
+    y = np.arange(n0, dtype=np.float64)[:, None]
+    x = np.arange(n1, dtype=np.float64)[None, :]
+    ref = 0.5 + 0.25 * (1.1 * np.cos(2 * np.pi * (12 * y / n0 - 10 * x / n1)) - np.cos(2 * np.pi * (9 * y / n0 + 14 * x / n1))) / 1.05
+    plan = EmulPlan((n0, n1))
+    spec, mx = plan.highpass_spectrum(ref)
+    want = o.highpassed_spectrum(ref)
+    assert np.abs(spec - want).max() < 1e-9 * want.max() and abs(mx - want.max()) < 1e-9 * mx
+    peaks = plan.find_peaks(ref)
+    opeaks = o.find_peaks(ref)
+    assert np.array_equal(np.array(peaks), np.array(opeaks))
+    carriers, cal = o.compute_carriers(ref, 3.0)
+    plan.bind(ref, peaks, carriers[0].radius, cal)
+    for i in range(2):
+        assert np.array_equal(plan.mask(i), carriers[i].mask)
+        assert np.abs(plan.ccsgn(i) - carriers[i].ccsgn).max() < 1e-12
+    # the unwrap and the residue count are shape-agnostic
+    w = np.angle(np.exp(1j * (0.15 * x + 0.05 * y + 3 * np.exp(-((y - 60) ** 2 + (x - 70) ** 2) / 800)))).astype(np.float32)
+    u = plan.unwrap_phase(w)
+    assert plan.count_residues(w[None]) == [0]
+    assert np.abs((u - w) / (2 * np.pi) - np.round((u - w) / (2 * np.pi))).max() < 1e-5
+    assert np.abs(u - o.unwrap_phase(w.astype(np.float64)) - (u - o.unwrap_phase(w.astype(np.float64)))[0, 0]).max() < 1e-4
     plan.close()

@@ -255,6 +255,67 @@ def test_drop_in_cache_survives_other_binds(api, golden):
     assert np.array_equal(hm_w, hm_w1) and rel_l2(hm_w, gb("height_map")) < 1e-5
 
 
+def plane_wave_board(n0, n1, p, q, uy=0.0, ux=0.0, eps=0.1):
+    """Exactly periodic two-carrier pattern on an n0 x n1 grid: integer cycle counts p = (rows, cols), q likewise."""
+    y = np.arange(n0, dtype=np.float64)[:, None] - uy
+    x = np.arange(n1, dtype=np.float64)[None, :] - ux
+    P = 2 * np.pi * (p[0] * y / n0 + p[1] * x / n1)
+    Q = 2 * np.pi * (q[0] * y / n0 + q[1] * x / n1)
+    return 0.5 + 0.25 * ((1 + eps) * np.cos(P) - np.cos(Q)) / (1 + eps / 2)
+
+
+@pytest.mark.parametrize("shape", [(600, 800), (375, 250)])
+def test_drop_in_any_shape(api, shape):
+    """The reference takes any image shape (pyfcd/fcd.py:14).  Shapes that are not powers of two run the float64
+    stage-level path (Bluestein transforms on the hand-written kernels, fcd_b200/generic.py): same carriers, same
+    calibration factor, height map and phases as the float64 oracle, clean and with residues, masked and batched."""
+    torch = api["torch"]
+    n0, n1 = shape
+    p, q = (round(0.055 * n0), round(0.005 * n1)), (-round(0.005 * n0), round(0.055 * n1))
+    ref = plane_wave_board(n0, n1, p, q)
+    y = np.arange(n0, dtype=np.float64)[:, None] - 0.45 * n0
+    x = np.arange(n1, dtype=np.float64)[None, :] - 0.55 * n1
+    sg = min(shape) / 7.0
+    g = np.exp(-(y * y + x * x) / (2 * sg * sg))
+    frames = []
+    for peak in (0.6, 4.5):                                       # no wrapping / wrapping
+        amp = peak * sg * np.exp(0.5)
+        frames.append(plane_wave_board(n0, n1, p, q, uy=amp * y / (sg * sg) * g, ux=amp * x / (sg * sg) * g))
+    noisy = frames[1] + 0.25 * np.random.default_rng(3).standard_normal(shape)
+    noisy[n0 // 3:n0 // 3 + n0 // 9, n1 // 4:n1 // 4 + n1 // 8] = 0.5
+    frames.append(noisy)
+    sq = 7.5
+    fcd, eng = api["fcd"], api["eng"]
+    carriers, cal = fcd.compute_carriers(ref, sq)
+    oc, ocal = o.compute_carriers(ref, sq)
+    assert cal == ocal and [c.pixels.tolist() for c in carriers] == [list(map(int, c.pixels)) for c in oc]
+    for a, b in zip(carriers, oc):
+        assert np.array_equal(a.mask, b.mask) and np.abs(a.ccsgn - b.ccsgn).max() < 1e-12
+    for k, fr in enumerate(frames):
+        hm, ph, c = fcd.compute_height_map(ref, fr, sq, height=0.8)
+        hmo, pho, _ = o.compute_height_map(ref, fr, sq, height=0.8)
+        assert c == ocal and hm.shape == shape and hm.dtype == np.float64 and hm.flags.writeable
+        assert rel_l2(hm, hmo) < (1e-9 if k < 2 else 1e-5), (k, rel_l2(hm, hmo))
+        for i in range(2):
+            assert phase_dev(ph[i], pho[i]) < (1e-8 if k < 2 else 1e-4)
+    plan = eng.get_plan(shape, 1)
+    assert not plan.fused
+    # batched API with a per-frame mask: reference substituted before, zeros after (analyze.py:231,255)
+    mask = np.zeros((3,) + shape, bool)
+    mask[:, n0 // 2:n0 // 2 + 40, n1 // 5:n1 // 5 + 60] = True
+    stack32 = np.stack(frames).astype(np.float32)              # camera frames are float32 (analyze.load_image)
+    maps, _, _ = eng.compute_height_maps(ref, stack32, sq, height=0.8, mask=torch.from_numpy(mask).cuda(), plan=plan)
+    guided = plan.last_guided_frames                            # the mask edge can add residues to the wrapping frame
+    assert 2 in guided and 0 not in guided
+    for k in range(3):
+        want, _, _ = o.compute_height_map(ref, np.where(mask[k], ref, stack32[k].astype(np.float64)), sq, height=0.8)
+        want *= ~mask[k]
+        assert rel_l2(maps[k].cpu().numpy(), want) < (1e-5 if k in guided else 1e-9), k
+        assert not maps[k].cpu().numpy()[mask[k]].any()
+    with pytest.raises(Exception):
+        plan.structure_mask(torch.from_numpy(frames[0].astype(np.float32)).cuda())        # fused plans only
+
+
 def test_plot_helpers_run_with_a_stub_matplotlib(api, golden, monkeypatch):
     """examples/fcd_example.py:21-22 call fcd.fft_peaks(reference) and compute_calibration_factor(..., plot=True).
     matplotlib is not installed here; a recording stub shows that both run and draw what the reference draws

@@ -176,6 +176,80 @@ struct SumKernel : NoPrologue {
     }
 };
 
+// ---- arbitrary sizes: Bluestein's chirp convolution around the power-of-two transforms ---------------------------
+// X[k] = c[k] * sum_n (x[n] c[n]) conj(c)[k - n],  c[n] = exp(-i pi n^2 / N)  -- a length-N DFT as a circular
+// convolution of length L >= 2N - 1 (a power of two).  In two dimensions the chirps are outer products, so one
+// padded (L0 x L1) forward transform, a multiplication by the precomputed spectrum of conj(c0) (x) conj(c1) and one
+// inverse transform give fft2 of any rows x cols image (scipy.fft.fft2 / ifft2 of the reference take any shape).
+struct BluParams {
+    const void* in;        // pad: [H][W] cx<double> (kind 0) | float (1) | double (2);  crop / mul: cd [L0][L1]
+    int in_kind;
+    double sub;            // subtracted from real input
+    cd* out;               // pad / mul: [L0][L1];  crop: [H][W]
+    const cd* c0;          // [H] chirp along rows
+    const cd* c1;          // [W] chirp along columns
+    const cd* fb;          // mul: spectrum of the chirp kernel [L0][L1]
+    int H, W, L0, L1;
+    int conj_io;           // inverse transform: conjugate the input (pad) / the output (crop)
+    double scale;
+    int nblocks;
+};
+struct BluPad : NoPrologue {
+    using Params = BluParams;
+    static constexpr bool BLOCKED_TILES = false;
+    static constexpr bool PIPELINED = false;
+    static constexpr int SYNC_THREADS = 0;
+    static constexpr int MIN_BLOCKS = 1;
+    static constexpr int THREADS = 256, PHASES = 1, SMEM_BYTES = 16;
+    struct State { int dummy; };
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
+        const long long n = (long long)p.L0 * p.L1;
+        for (long long i = (long long)bx * THREADS + tid; i < n; i += (long long)p.nblocks * THREADS) {
+            const int r = (int)(i / p.L1), c = (int)(i % p.L1);
+            cd v = mk<double>(0.0, 0.0);
+            if (r < p.H && c < p.W) {
+                const long long j = (long long)r * p.W + c;
+                if (p.in_kind == 0) v = reinterpret_cast<const cd*>(p.in)[j];
+                else if (p.in_kind == 1) v = mk<double>((double)reinterpret_cast<const float*>(p.in)[j] - p.sub, 0.0);
+                else v = mk<double>(reinterpret_cast<const double*>(p.in)[j] - p.sub, 0.0);
+                if (p.conj_io) v = conj(v);
+                v = v * (p.c0[r] * p.c1[c]);
+            }
+            p.out[i] = v;
+        }
+    }
+};
+struct BluMul : BluPad {
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
+        const long long n = (long long)p.L0 * p.L1;
+        for (long long i = (long long)bx * THREADS + tid; i < n; i += (long long)p.nblocks * THREADS)
+            p.out[i] = reinterpret_cast<const cd*>(p.in)[i] * p.fb[i];
+    }
+};
+// out = (outer product of two vectors), used once per plan for the chirp kernel conj(c0) (x) conj(c1)
+struct BluOuter : BluPad {
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
+        const long long n = (long long)p.L0 * p.L1;
+        for (long long i = (long long)bx * THREADS + tid; i < n; i += (long long)p.nblocks * THREADS)
+            p.out[i] = p.c0[i / p.L1] * p.c1[i % p.L1];
+    }
+};
+struct BluCrop : BluPad {
+    template <int PH>
+    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char*, State&) {
+        const long long n = (long long)p.H * p.W;
+        for (long long i = (long long)bx * THREADS + tid; i < n; i += (long long)p.nblocks * THREADS) {
+            const int r = (int)(i / p.W), c = (int)(i % p.W);
+            cd v = reinterpret_cast<const cd*>(p.in)[(long long)r * p.L1 + c] * (p.c0[r] * p.c1[c]);
+            if (p.conj_io) v = conj(v);
+            p.out[i] = scale(v, p.scale);
+        }
+    }
+};
+
 // float64 image -> float32 copy (the reference image as the masked workflow substitutes it, analyze.py:231)
 struct NarrowParams {
     const double* in;
@@ -223,7 +297,7 @@ struct SpecMag : NoPrologue {
         double best = 0.0;
         for (long long i = (long long)bx * THREADS + tid; i < n; i += (long long)p.nblocks * THREADS) {
             const int r = (int)(i / p.W), c = (int)(i % p.W);
-            int kr = (r + p.H / 2) % p.H, kc = (c + p.W / 2) % p.W;   // unshifted index of shifted (r,c)
+            int kr = (r + p.H - p.H / 2) % p.H, kc = (c + p.W - p.W / 2) % p.W;   // unshifted index of shifted (r,c), odd sizes too
             if (kc > p.W / 2) { kr = (p.H - kr) % p.H; kc = p.W - kc; }
             const cd z = p.spec[(long long)kr * p.W + kc];
             double m = hypot(z.x, z.y);

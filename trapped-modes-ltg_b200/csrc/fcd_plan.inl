@@ -108,21 +108,72 @@ struct PlanImpl {
     rt::StageTimer timer;
 
     // ------------------------------------------------------------------ construction ----
+    // Two kinds of plan.  FUSED: rows and cols powers of two in [64, 4096] -- the float32 pipeline K1..K5 and everything
+    // around it.  GENERIC: any other shape with 2 <= rows, cols <= 2048 (the reference takes any shape, pyfcd/fcd.py:14):
+    // the float64 per-reference path (carrier search, masks, ccsgn), fcd_fft2_c128, the unwrap and the residue count
+    // work through Bluestein's chirp convolution on padded power-of-two transforms; the host layer builds the
+    // per-frame path from those stage-level pieces (fcd_b200/generic.py).  fcd_execute and the structure-mask entry
+    // points need a fused plan.
+    bool generic = false;
+    int L0 = 0, L1 = 0;                       // generic: padded transform sizes (powers of two >= 2N - 1)
+    rt::DevBuf<cd> blu_c0, blu_c1, blu_fb, blu_a;
+
+    static int blu_length(int n) {
+        int l = 64;
+        while (l < 2 * n - 1) l *= 2;
+        return l;
+    }
+    static std::vector<cd> chirp(int n, int len, bool kernel) {
+        // kernel == false: c[m] = exp(-i pi m^2 / n), m < n.  kernel == true: conj(c)[m] for |m| < n laid out circularly
+        // in `len` slots.  m^2 is reduced mod 2n in integers so that the angle keeps full precision.
+        std::vector<cd> v((size_t)(kernel ? len : n), mk<double>(0.0, 0.0));
+        for (int m = 0; m < n; ++m) {
+            const long long q = ((long long)m * m) % (2LL * n);
+            const long double ang = 3.14159265358979323846264338327950288L * (long double)q / (long double)n;
+            const cd w = mk<double>((double)cosl(ang), (double)(kernel ? sinl(ang) : -sinl(ang)));
+            v[(size_t)m] = w;
+            if (kernel && m) v[(size_t)(len - m)] = w;
+        }
+        return v;
+    }
+    void require_fused(const char* what) const {
+        if (generic) rt::fail(std::string(what) + " needs a plan whose rows and cols are powers of two in [64, 4096]");
+    }
+
     void init(int rows, int cols, int frames_per_launch) {
-        if (!supported_dim(rows) || !supported_dim(cols))
-            rt::fail("unsupported shape: rows and cols must be powers of two in [64, 4096]");
         if (frames_per_launch < 1 || frames_per_launch > 16384) rt::fail("frames_per_launch out of range");
+        generic = !(supported_dim(rows) && supported_dim(cols));
+        if (generic && (rows < 2 || cols < 2 || rows > 2048 || cols > 2048))
+            rt::fail("unsupported shape: rows and cols must be powers of two in [64, 4096] (fused float32 pipeline) "
+                     "or anything in [2, 2048] (float64 stage-level path)");
         H = rows; W = cols; chunk = frames_per_launch;
         sms = rt::sm_count();
-        FCD_DISPATCH_L(W, {
-            tw_w_f.upload(Fft<L, -1, float>::make_table(), nullptr);
+        L0 = generic ? blu_length(H) : H;
+        L1 = generic ? blu_length(W) : W;
+        FCD_DISPATCH_L(L1, {
+            if (!generic) tw_w_f.upload(Fft<L, -1, float>::make_table(), nullptr);
             tw_w_d.upload(Fft<L, -1, double>::make_table(), nullptr);
         })
-        FCD_DISPATCH_L(H, {
-            tw_h_f.upload(Fft<L, -1, float>::make_table(), nullptr);
+        FCD_DISPATCH_L(L0, {
+            if (!generic) tw_h_f.upload(Fft<L, -1, float>::make_table(), nullptr);
             tw_h_d.upload(Fft<L, -1, double>::make_table(), nullptr);
         })
         w4p = W / 2 + 4;
+        if (generic) {
+            blu_c0.upload(chirp(H, L0, false), nullptr);
+            blu_c1.upload(chirp(W, L1, false), nullptr);
+            rt::DevBuf<cd> k0, k1;
+            k0.upload(chirp(H, L0, true), nullptr);
+            k1.upload(chirp(W, L1, true), nullptr);
+            const size_t n = (size_t)L0 * L1;
+            blu_fb.alloc(n);
+            blu_a.alloc(n);
+            const int nb = elem_blocks((long long)n);
+            BluParams bp{nullptr, 0, 0.0, blu_fb.ptr, k0.ptr, k1.ptr, nullptr, H, W, L0, L1, 0, 1.0, nb};
+            launch<BluOuter>(nb, 1, nullptr, bp);
+            fft2_pow2(blu_fb.ptr, 0, 0.0, blu_fb.ptr, -1, L0, L1, nullptr);
+            rt::sync(nullptr);
+        }
     }
 
     void ensure_reference_scratch() {
@@ -132,20 +183,39 @@ struct PlanImpl {
     }
 
     // ------------------------------------------------------------------ float64 fft2 ----
+    // power-of-two transform of a rows x cols array with the plan's tables (rows == L0, cols == L1)
+    void fft2_pow2(const void* in, int kind, double sub, cd* out, int dir, int rows, int cols, rt::stream_t s) {
+        FCD_DISPATCH_L(cols, {
+            constexpr int G = Tune<L>::GGEN;
+            GenRowsParams<double> p{in, kind, sub, out, tw_w_d.ptr, rows, 1.0};
+            if (dir < 0) launch<GenRows<L, G, -1, double>>(ceil_div(rows, G), 1, s, p);
+            else launch<GenRows<L, G, +1, double>>(ceil_div(rows, G), 1, s, p);
+        })
+        FCD_DISPATCH_L(rows, {
+            constexpr int G = Tune<L>::GGEN;
+            GenColsParams<double> p{out, out, tw_h_d.ptr, cols, dir < 0 ? 1.0 : 1.0 / ((double)rows * cols)};
+            if (dir < 0) launch<GenCols<L, G, -1, double>>(ceil_div(cols, G), 1, s, p);
+            else launch<GenCols<L, G, +1, double>>(ceil_div(cols, G), 1, s, p);
+        })
+    }
     // out = fft2(in) (dir=-1) or ifft2(in) (dir=+1, scaled 1/(HW)); in may alias out for kind 0
     void fft2_d(const void* in, int kind, double sub, cd* out, int dir, rt::stream_t s) {
-        FCD_DISPATCH_L(W, {
-            constexpr int G = Tune<L>::GGEN;
-            GenRowsParams<double> p{in, kind, sub, out, tw_w_d.ptr, H, 1.0};
-            if (dir < 0) launch<GenRows<L, G, -1, double>>(ceil_div(H, G), 1, s, p);
-            else launch<GenRows<L, G, +1, double>>(ceil_div(H, G), 1, s, p);
-        })
-        FCD_DISPATCH_L(H, {
-            constexpr int G = Tune<L>::GGEN;
-            GenColsParams<double> p{out, out, tw_h_d.ptr, W, dir < 0 ? 1.0 : 1.0 / ((double)H * W)};
-            if (dir < 0) launch<GenCols<L, G, -1, double>>(ceil_div(W, G), 1, s, p);
-            else launch<GenCols<L, G, +1, double>>(ceil_div(W, G), 1, s, p);
-        })
+        if (!generic) {
+            fft2_pow2(in, kind, sub, out, dir, H, W, s);
+            return;
+        }
+        // Bluestein in two dimensions; ifft2(x) = conj(fft2(conj(x))) / (H W)
+        const int nb = elem_blocks((long long)L0 * L1);
+        BluParams bp{in, kind, sub, blu_a.ptr, blu_c0.ptr, blu_c1.ptr, blu_fb.ptr, H, W, L0, L1, dir > 0 ? 1 : 0, 1.0, nb};
+        launch<BluPad>(nb, 1, s, bp);
+        fft2_pow2(blu_a.ptr, 0, 0.0, blu_a.ptr, -1, L0, L1, s);
+        bp.in = blu_a.ptr;
+        launch<BluMul>(nb, 1, s, bp);
+        fft2_pow2(blu_a.ptr, 0, 0.0, blu_a.ptr, +1, L0, L1, s);
+        bp.out = out;
+        bp.scale = dir > 0 ? 1.0 / ((double)H * W) : 1.0;
+        bp.nblocks = elem_blocks((long long)H * W);
+        launch<BluCrop>(bp.nblocks, 1, s, bp);
     }
 
     int sms = 148;   // multiprocessors of the plan's device (init)
@@ -347,12 +417,14 @@ struct PlanImpl {
         }
         det = f[0][1] * f[1][0] - f[0][0] * f[1][1];                 // fcd.py:134-135
 
-        // wavenumber vectors of integrate_in_fourier with the N//2+1 quirk (fourier.py:128-132)
-        std::vector<float> vkx(W), vkxq(W);
-        for (int j = 0; j < W; ++j) { vkx[j] = (float)fftfreq_at(W, d, j); vkxq[j] = vkx[j]; }
-        vkxq[W / 2 + 1] = 0.f;
-        kx.upload(vkx, s); kxq.upload(vkxq, s);
-        dky = (float)fftfreq_at(H, d, 1);
+        // wavenumber vectors of integrate_in_fourier with the N//2+1 quirk (fourier.py:128-132); fused plans only
+        if (!generic) {
+            std::vector<float> vkx(W), vkxq(W);
+            for (int j = 0; j < W; ++j) { vkx[j] = (float)fftfreq_at(W, d, j); vkxq[j] = vkx[j]; }
+            vkxq[W / 2 + 1] = 0.f;
+            kx.upload(vkx, s); kxq.upload(vkxq, s);
+            dky = (float)fftfreq_at(H, d, 1);
+        }
 
         // ccsgn_i = conj(ifft2(fft2(ref) * mask_i))   (carriers.py:22-24), float64 then stored c64
         fft2_d(ref, is_f64 ? 2 : 1, 0.0, spec.ptr, -1, s);
@@ -367,13 +439,15 @@ struct PlanImpl {
                                                          theta.ptr + (size_t)i * n, n, nb});
         }
 
-        // workspaces
-        w1.alloc((size_t)chunk * 2 * ncp * H);
-        w2.alloc((size_t)chunk * 2 * ncp * H);
-        w3.alloc((size_t)chunk * w3_blocks(W) * H * 4);
-        w4.alloc((size_t)chunk * H * w4p);
-        colphase.alloc((size_t)chunk * 2 * H);
-        rowoff.alloc((size_t)chunk * 2 * H);
+        // workspaces of the fused pipeline
+        if (!generic) {
+            w1.alloc((size_t)chunk * 2 * ncp * H);
+            w2.alloc((size_t)chunk * 2 * ncp * H);
+            w3.alloc((size_t)chunk * w3_blocks(W) * H * 4);
+            w4.alloc((size_t)chunk * H * w4p);
+            colphase.alloc((size_t)chunk * 2 * H);
+            rowoff.alloc((size_t)chunk * 2 * H);
+        }
         rt::sync(s);
         bound = true;
     }
@@ -520,6 +594,7 @@ struct PlanImpl {
 
     void execute(const void* frames, int frame_kind, int n_frames, float* height_out, float* phases,
                  const uint8_t* mask, long long mask_stride, int unwrap, rt::stream_t s) {
+        require_fused("fcd_execute (the fused float32 pipeline)");
         if (frame_kind < 0 || frame_kind > 2) rt::fail("frame dtype must be 0 (float32), 1 (uint8) or 2 (uint16)");
         if (unwrap < 0 || unwrap > 3) rt::fail("unwrap must be 0 (off), 1 (scan), 2 (reliability-guided) or 3 (auto)");
         const size_t px = frame_kind == 0 ? 4 : (frame_kind == 1 ? 1 : 2);
@@ -875,6 +950,7 @@ struct PlanImpl {
     }
 
     void structure_mask(const float* frames, int n_frames, int smoothed, uint8_t* mask_out, rt::stream_t s) {
+        require_fused("fcd_structure_mask");
         if (smoothed < 1 || smoothed > std::min(H, W)) rt::fail("smoothed must be in [1, min(rows, cols)]");
         mask_workspace(false);
         const long long n = (long long)H * W;
@@ -909,6 +985,7 @@ struct PlanImpl {
     }
 
     void mask_center(const uint8_t* mask, int n_frames, int* centers_host, rt::stream_t s) {
+        require_fused("fcd_mask_center");
         mask_workspace(true);
         const long long n = (long long)H * W;
         for (int f0 = 0; f0 < n_frames; f0 += mask_chunk()) {
@@ -1186,5 +1263,6 @@ int fcd_last_auto(const fcd_plan* plan, long long* flagged_out, int* guided_coun
 
 long long fcd_launch_count(const fcd_plan* plan) { return plan ? plan->impl.launches : 0; }
 int fcd_band_columns(const fcd_plan* plan) { return plan ? plan->impl.ncp : 0; }
+int fcd_plan_is_fused(const fcd_plan* plan) { return plan && !plan->impl.generic ? 1 : 0; }
 
 }  // extern "C"

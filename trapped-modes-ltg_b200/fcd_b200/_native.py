@@ -62,6 +62,7 @@ PROTOTYPES = {
     "fcd_last_auto": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong), c_int_p, c_int_p, ctypes.c_int]),
     "fcd_launch_count": (ctypes.c_longlong, [ctypes.c_void_p]),
     "fcd_band_columns": (ctypes.c_int, [ctypes.c_void_p]),
+    "fcd_plan_is_fused": (ctypes.c_int, [ctypes.c_void_p]),
 }
 
 

@@ -139,6 +139,8 @@ class HeightMapPlan:
         with torch.cuda.device(self.device):
             check(self.lib, self.lib.fcd_plan_create(self.shape[0], self.shape[1], self.frames_per_launch,
                                                      ctypes.byref(self._h)))
+        self.fused = bool(self.lib.fcd_plan_is_fused(self._h))   # False: a shape that is not a power of two (generic.py)
+        self._generic = None
         self.peaks = None
         self.radius = None
         self.calibration_factor = None
@@ -222,6 +224,7 @@ class HeightMapPlan:
         self.peaks, self.radius = peaks, float(radius)
         self.calibration_factor, self.height = float(calibration_factor), h_eff
         self._reference = ref
+        self._generic = None
         return self.calibration_factor
 
     def carrier_frequencies(self):
@@ -248,6 +251,8 @@ class HeightMapPlan:
         ``unwrap``: see :func:`unwrap_mode`."""
         mode = unwrap_mode(unwrap)
         kinds = {torch.float32: 0, torch.uint8: 1, torch.uint16: 2}
+        if not self.fused:
+            kinds[torch.float64] = 3          # the float64 path of generic plans takes float64 frames as they are
         if not (isinstance(frames, torch.Tensor) and frames.is_cuda and frames.dtype in kinds):
             raise TypeError("frames must be a CUDA float32 / uint8 / uint16 tensor "
                             "(see compute_height_maps for numpy input)")
@@ -259,19 +264,21 @@ class HeightMapPlan:
         fr = fr.contiguous()
         self._check_image(fr)
         n = fr.shape[0]
+        # generic plans (shapes that are not powers of two) compute in float64 and hand out float64 by default
+        odt = (torch.float32,) if self.fused else (torch.float64, torch.float32)
         if out is None:
-            out = torch.empty(fr.shape, dtype=torch.float32, device=fr.device)
-        elif not (out.is_cuda and out.device == self.device and out.dtype == torch.float32 and out.is_contiguous()
+            out = torch.empty(fr.shape, dtype=odt[0], device=fr.device)
+        elif not (out.is_cuda and out.device == self.device and out.dtype in odt and out.is_contiguous()
                   and out.numel() == fr.numel()):
             raise ValueError("out must be a contiguous CUDA float32 tensor of the frames' size on the plan's device")
         ph = None
         if isinstance(phases, torch.Tensor):
             ph = phases
-            if not (ph.is_cuda and ph.device == self.device and ph.dtype == torch.float32 and ph.is_contiguous()
+            if not (ph.is_cuda and ph.device == self.device and ph.dtype in odt and ph.is_contiguous()
                     and tuple(ph.shape) == (n, 2) + self.shape):
                 raise ValueError("phases must be a contiguous CUDA float32 tensor [n, 2, H, W] on the plan's device")
         elif phases:
-            ph = torch.empty((n, 2) + self.shape, dtype=torch.float32, device=self.device)
+            ph = torch.empty((n, 2) + self.shape, dtype=odt[0], device=self.device)
         mask_stride = 0
         mk = None
         if mask is not None:
@@ -281,6 +288,19 @@ class HeightMapPlan:
                     raise ValueError("per-frame mask count differs from frame count")
                 mask_stride = self.shape[0] * self.shape[1]
             self._check_image(mk)
+        if not self.fused:
+            if self.peaks is None:
+                raise _native.FcdError(_native.FCD_ERR_STATE, "execute called before bind")
+            if self._generic is None:
+                from .generic import GenericPipeline
+                self._generic = GenericPipeline(self)
+            with torch.cuda.device(self.device):
+                guided = self._generic.execute(fr, out.view((n,) + self.shape), ph, mk, mode)
+            self.last_guided_frames, self.last_flagged_frames = guided, len(guided)
+            if squeeze:
+                out = out.view(self.shape)
+                ph = ph[0] if ph is not None else None
+            return (out, ph) if ph is not None else out
         with torch.cuda.device(self.device):
             check(self.lib, self.lib.fcd_execute_typed(self._h, _ptr(fr), kind, int(n), _ptr(out), _ptr(ph),
                                                        _ptr(mk), int(mask_stride), mode, _stream_ptr()))
@@ -417,7 +437,7 @@ def compute_height_maps(reference, frames, square_size, layers=None, height=None
     elif isinstance(frames, np.ndarray) and frames.dtype in (np.uint8, np.uint16):
         fr = torch.from_numpy(np.ascontiguousarray(frames)).to(plan.device)    # widened on the GPU
     else:
-        fr = to_device_image(frames, plan.device, allow_f64=False)
+        fr = to_device_image(frames, plan.device, allow_f64=not plan.fused)
     res = plan.execute(fr, out=out, phases=return_phases, mask=mask, unwrap=unwrap)
     if return_phases:
         return res[0], res[1], cal

@@ -5,6 +5,7 @@ import numpy as np
 import torch
 
 from fcd_b200 import engine as _eng
+from fcd_b200.generic import unwrap_scan as _unwrap_scan
 from pyfcd.fourier import fourier
 from pyfcd.carriers import Carrier
 
@@ -19,7 +20,8 @@ class fcd:
         float64); `phases` equal the reference's up to one global 2*pi*k per map.
         unwrap=True follows the reference's unwrapper: the scan path where the wrapped phases
         have no residues (every path gives the same answer there), the reliability-guided
-        device unwrap (csrc/fcd_unwrap.cuh) where they do."""
+        device unwrap (csrc/fcd_unwrap.cuh) where they do.  Shapes that are not powers of two take the float64
+        stage-level path (fcd_b200/generic.py)."""
         height = _eng.resolve_height(layers, height)
         plan = _eng.get_plan(np.shape(reference), 1)
         # The reference recomputes the carriers on every call (fcd.py:27).  Callers loop over
@@ -36,7 +38,7 @@ class fcd:
             plan._dropin_key = None
             calibration_factor = plan.bind(ref_dev, square_size=square_size, height=height)
             plan._dropin_key = (ref_dev, float(square_size))
-        frame = _eng.to_device_image(displaced, plan.device, allow_f64=False)
+        frame = _eng.to_device_image(displaced, plan.device, allow_f64=not plan.fused)
         # the reference does `if unwrap:` (fcd.py:119): any truthy non-string value means its unwrapper
         mode = unwrap if isinstance(unwrap, str) else ("auto" if bool(unwrap) else False)
         height_map, phases = plan.execute(frame, phases=True, unwrap=mode)
@@ -144,20 +146,3 @@ class fcd:
         ax.legend()
         plt.tight_layout()
         plt.show()
-
-
-def _unwrap_scan(w: torch.Tensor) -> torch.Tensor:
-    """Row/column path unwrap on the device, anchored at the centre pixel (same path as the
-    fused kernels: RowDemod + RowLink in csrc/fcd_kernels.cuh)."""
-    two_pi = 2.0 * np.pi
-    n0, n1 = w.shape
-    jr = torch.zeros_like(w, dtype=torch.int64)
-    jr[:, 1:] = torch.round((w[:, 1:] - w[:, :-1]) / two_pi).to(torch.int64)
-    c = torch.cumsum(jr, dim=1)
-    c = c - c[:, n1 // 2:n1 // 2 + 1]
-    col = w[:, n1 // 2]
-    jc = torch.zeros(n0, dtype=torch.int64, device=w.device)
-    jc[1:] = torch.round((col[1:] - col[:-1]) / two_pi).to(torch.int64)
-    m = torch.cumsum(jc, dim=0)
-    m = m - m[n0 // 2]
-    return w - two_pi * (c + m[:, None]).to(w.dtype)
