@@ -358,8 +358,8 @@ struct ColBandParams {
 
 template <int L, int G>
 struct ColBand : AllPhases {
-    using FF = Fft<L, -1, float>;
-    using FI = Fft<L, +1, float>;
+    using FF = Fft<L, -1, float, ColPlan<L>>;
+    using FI = Fft<L, +1, float, ColPlan<L>>;
     using GL = GroupLayout<L, G>;
     using Params = ColBandParams;
     static constexpr bool BLOCKED_TILES = false;
@@ -899,8 +899,8 @@ struct ColIntegrateParams {
 
 template <int L, int G>
 struct ColIntegrate : AllPhases {
-    using FF = Fft<L, -1, float>;
-    using FI = Fft<L, +1, float>;
+    using FF = Fft<L, -1, float, ColPlan<L>>;
+    using FI = Fft<L, +1, float, ColPlan<L>>;
     using GL = GroupLayout<L, G, 2>;
     using Params = ColIntegrateParams;
     static constexpr bool BLOCKED_TILES = false;

@@ -155,7 +155,7 @@ struct PlanImpl {
             tw_w_d.upload(Fft<L, -1, double>::make_table(), nullptr);
         })
         FCD_DISPATCH_L(L0, {
-            if (!generic) tw_h_f.upload(Fft<L, -1, float>::make_table(), nullptr);
+            if (!generic) tw_h_f.upload(Fft<L, -1, float, ColPlan<L>>::make_table(), nullptr);   // K2, K4
             tw_h_d.upload(Fft<L, -1, double>::make_table(), nullptr);
         })
         w4p = W / 2 + 4;

@@ -183,6 +183,16 @@ template <> struct Plan<1024> { static constexpr int R1 = 8,  R2 = 8,  R3 = 16; 
 template <> struct Plan<2048> { static constexpr int R1 = 8,  R2 = 16, R3 = 16; };
 template <> struct Plan<4096> { static constexpr int R1 = 16, R2 = 16, R3 = 16; };
 
+// Radix order of the COLUMN kernels (K2, K4), whose warps hold a few consecutive rows of SEVERAL transforms (lanes =
+// 32/G rows x G columns, so that a warp request covers whole sectors of the column-blocked planes).  With that lane
+// mapping the scatter of a radix-8 first pass hits every bank twice (16 of K4's 80 shared-memory instructions per
+// transform, 18 % of its wavefronts in ncu); a radix-16 first pass writes rows 17 slots apart and is conflict free, like
+// every other access pattern of both orders (simulated for the half-warp x bank matrix; ncu confirms).
+template <int L> struct ColPlan : Plan<L> {};
+template <> struct ColPlan<2048> { static constexpr int R1 = 16, R2 = 8, R3 = 16; };
+template <> struct ColPlan<1024> { static constexpr int R1 = 16, R2 = 8, R3 = 8; };
+template <> struct ColPlan<512>  { static constexpr int R1 = 16, R2 = 4, R3 = 8; };
+
 // smem slot of logical element p: one pad element per 16 (keeps radix-strided writes of
 // the first pass and 16-aligned runs of the later passes bank-conflict free)
 FCD_HD int fft_pos(int p) { return p + (p >> 4); }
