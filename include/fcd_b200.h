@@ -72,8 +72,8 @@ int fcd_bind_reference(fcd_plan* plan, const void* reference_dev, int reference_
  * 2 = reliability-guided like scikit-image, see fcd_unwrap_phase;
  * 3 = "auto", what the drop-in's unwrap=True runs: the scan path, during which the demodulation kernel flags
  * every frame that has |phase| > pi/2 somewhere -- only those can hold a 2*pi jump, let alone a residue; the
- * flagged frames get their wrapped phases materialised and their residues counted, and the frames that hold
- * residues are redone exactly as mode 2 would; frames without residues keep the scan result, where every
+ * flags are read back once per call (4 bytes per frame), the flagged frames get their wrapped phases
+ * materialised and their residues counted, and the frames that hold residues are redone exactly as mode 2 would; frames without residues keep the scan result, where every
  * unwrapper yields the same integers.  fcd_last_auto reports what happened)
  * -> compute_displacement_field (fcd.py:123-138) -> -u/height -> integrate_in_fourier
  * (fourier.py:116-137).  Optional mask_dev (uint8, nonzero = masked): the frame is replaced

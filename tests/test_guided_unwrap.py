@@ -100,6 +100,10 @@ def test_emulated_auto_mode_flags_probes_and_redoes_only_what_it_must(golden):
         assert np.array_equal(h3[i], h1[i]) and np.array_equal(p3[i], p1[i])
     for i in (1, 3, 4):
         assert np.array_equal(h3[i], h2[i]) and np.array_equal(p3[i], p2[i])
+    # flagged frames that are consecutive are probed where they lie (no gather): same results
+    h3c, p3c = plan.execute(frames[1:5], phases=True, unwrap=3)
+    assert plan.last_auto() == (4, [0, 2, 3])
+    assert np.array_equal(h3c, h3[1:5]) and np.array_equal(p3c, p3[1:5])
     # without a phases buffer the same height maps come out, and a per-frame mask follows its frame
     assert np.array_equal(plan.execute(frames, unwrap=3), h3)
     mask = np.zeros(frames.shape, np.uint8)

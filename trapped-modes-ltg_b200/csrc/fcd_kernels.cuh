@@ -247,7 +247,7 @@ struct RowFwdParams {
 
 template <int L, int G>
 struct RowFwd : AllPhases {
-    using F = Fft<L, -1, float>;
+    using F = Fft<L, -1, float, RowPlan<L>>;
     using GL = GroupLayout<L, G>;
     using Params = RowFwdParams;
     static constexpr bool BLOCKED_TILES = false;
@@ -487,8 +487,8 @@ struct int2s { int a, b; };
 
 template <int L, int G, bool PRUNED = false>
 struct RowDemod {
-    using FF = Fft<L, -1, float>;
-    using FI = Fft<L, +1, float>;
+    using FF = Fft<L, -1, float, RowPlan<L>>;
+    using FI = Fft<L, +1, float, RowPlan<L>>;
     using GL = GroupLayout<L, G, 2>;
     using Params = RowDemodParams;
     static constexpr bool BLOCKED_TILES = true;
@@ -1053,7 +1053,7 @@ struct RowInvParams {
 
 template <int L, int G>
 struct RowInv : AllPhases {
-    using FI = Fft<L, +1, float>;
+    using FI = Fft<L, +1, float, RowPlan<L>>;
     using GL = GroupLayout<L, G>;
     using Params = RowInvParams;
     static constexpr bool BLOCKED_TILES = false;

@@ -151,7 +151,7 @@ struct PlanImpl {
         L0 = generic ? blu_length(H) : H;
         L1 = generic ? blu_length(W) : W;
         FCD_DISPATCH_L(L1, {
-            if (!generic) tw_w_f.upload(Fft<L, -1, float>::make_table(), nullptr);
+            if (!generic) tw_w_f.upload(Fft<L, -1, float, RowPlan<L>>::make_table(), nullptr);   // K1, K3, K5
             tw_w_d.upload(Fft<L, -1, double>::make_table(), nullptr);
         })
         FCD_DISPATCH_L(L0, {
@@ -488,7 +488,7 @@ struct PlanImpl {
             RowDemodParams p{w2.ptr + (size_t)wf * 2 * H * ncp, theta.ptr, w3.ptr, colphase.ptr, po, tw_w_f.ptr, H, ncp,
                              {nc[0], nc[1]}, {c_lo[0] - W / 2, c_lo[1] - W / 2}, W / 2, scan, flags};
             bool pruned = false;
-            if constexpr (Plan<L>::R1 == 8) {
+            if constexpr (RowPlan<L>::R1 == 8) {
                 if (nc[0] <= L / 8 && nc[1] <= L / 8) {
                     pruned = true;
                     launch<RowDemod<L, G, true>>(nf, H / G, s, p);
@@ -551,26 +551,43 @@ struct PlanImpl {
     std::vector<int> auto_guided;             // frames whose phases held residues (redone reliability-guided)
     static constexpr int kProbe = 16;         // frames per residue probe (bounds the phase scratch)
 
-    // Frames [w0, w0 + a.nf) of the call: after the scan pass, look again at the frames K3 flagged.  Their wrapped
-    // phases are materialised (K3 once more on the wave's band-passed spectra, into scratch), residues counted, and only frames that hold any
-    // are unwrapped along the reliability-guided tree and re-integrated -- bit for bit what unwrap = 2 does.
-    // A frame without residues keeps its scan result: there every unwrapper gives the same integers.
-    void auto_second_look(const Wave& a, int w0, float* po_user, rt::stream_t s) {
+    // Second look of unwrap "auto", once per call: `idx` are the frames K3 flagged (ascending).  They are taken in
+    // batches of kProbe; a batch whose frames are consecutive is used where it lies, any other batch is first copied
+    // together (one device-to-device copy per frame: flagged frames that are few and far between still fill whole
+    // launches) and its results copied back.  Per batch: K1-K3 without unwrap -> wrapped phases in scratch, residues
+    // counted, and only the frames that hold residues are unwrapped along the reliability-guided tree and
+    // re-integrated -- bit for bit what unwrap = 2 does.  A frame without residues keeps its scan result: there
+    // every unwrapper gives the same integers.
+    rt::DevBuf<unsigned char> g_frames, g_mask;
+    rt::DevBuf<float> g_out;
+    void auto_second_look(const std::vector<int>& idx, const void* frames, int kind, float* height_out, float* phases,
+                          const uint8_t* mask, long long mask_stride, rt::stream_t s) {
         const long long n = (long long)H * W;
-        std::vector<int> flags((size_t)a.nf);
-        rt::d2h(flags.data(), frameflag.ptr, sizeof(int) * (size_t)a.nf, s);
-        int i = 0;
-        while (i < a.nf) {
-            if (!flags[i]) { ++i; continue; }
-            int j = i;
-            while (j < a.nf && flags[j] && j - i < kProbe) ++j;
-            const int m = j - i;                                  // run of flagged frames [i, j)
+        const size_t px = kind == 0 ? 4 : (kind == 1 ? 1 : 2);
+        const int batch = std::min(kProbe, chunk);
+        ph_ws.grow((size_t)kProbe * 2 * n);
+        res_counts.grow((size_t)2 * kProbe);
+        for (size_t b0 = 0; b0 < idx.size(); b0 += (size_t)batch) {
+            const int m = (int)std::min<size_t>((size_t)batch, idx.size() - b0);
+            const int* id = idx.data() + b0;
             auto_flagged += m;
-            ph_ws.grow((size_t)kProbe * 2 * n);
+            const bool inplace = id[m - 1] - id[0] == m - 1;
+            Wave sub;
+            if (inplace) {
+                sub = Wave{static_cast<const unsigned char*>(frames) + (size_t)id[0] * n * px, kind, m,
+                           height_out + (long long)id[0] * n, mask ? mask + (long long)id[0] * mask_stride : nullptr, mask_stride};
+            } else {
+                g_frames.grow((size_t)kProbe * n * px);
+                g_out.grow((size_t)kProbe * n);
+                if (mask && mask_stride) g_mask.grow((size_t)kProbe * n);
+                for (int j = 0; j < m; ++j) {
+                    rt::d2d(g_frames.ptr + (size_t)j * n * px, static_cast<const unsigned char*>(frames) + (size_t)id[j] * n * px, n * px, s);
+                    if (mask && mask_stride) rt::d2d(g_mask.ptr + (size_t)j * n, mask + (long long)id[j] * mask_stride, (size_t)n, s);
+                }
+                sub = Wave{g_frames.ptr, kind, m, g_out.ptr, mask ? (mask_stride ? g_mask.ptr : mask) : nullptr, mask_stride};
+            }
             if (profiling) timer.begin_chunk(s, m);
-            const Wave sub = sub_wave(a, i, m, n);
-            stage_demod(i, m, ph_ws.ptr, 0, nullptr, s);          // wrapped phases of the run -> scratch (w2 is still the wave's)
-            res_counts.grow((size_t)2 * kProbe);
+            stage_front(sub, ph_ws.ptr, 0, nullptr, s);           // wrapped phases of the batch -> scratch
             rt::dmemset(res_counts.ptr, 0, sizeof(int) * 2 * kProbe, s);
             launch<ResidueCount>(H - 1, 2 * m, s, ResidueParams{ph_ws.ptr, res_counts.ptr, H, W});
             int counts[2 * kProbe];
@@ -580,15 +597,17 @@ struct PlanImpl {
                 if (!(counts[2 * q] || counts[2 * q + 1])) { ++q; continue; }
                 int r = q;
                 while (r < m && (counts[2 * r] || counts[2 * r + 1])) ++r;
-                stage_guided(ph_ws.ptr, q, r - q, s);              // frames [q, r) of the run
+                stage_guided(ph_ws.ptr, q, r - q, s);              // frames [q, r) of the batch
                 stage_back(sub, q, r - q, 0, s);
-                if (po_user)
-                    rt::d2d(po_user + (long long)(i + q) * 2 * n, ph_ws.ptr + (long long)q * 2 * n,
-                            sizeof(float) * (size_t)(r - q) * 2 * n, s);
-                for (int k = q; k < r; ++k) auto_guided.push_back(w0 + i + k);
+                for (int k = q; k < r; ++k) {
+                    if (!inplace)
+                        rt::d2d(height_out + (long long)id[k] * n, g_out.ptr + (long long)k * n, sizeof(float) * (size_t)n, s);
+                    if (phases)
+                        rt::d2d(phases + (long long)id[k] * 2 * n, ph_ws.ptr + (long long)k * 2 * n, sizeof(float) * (size_t)(2 * n), s);
+                    auto_guided.push_back(id[k]);
+                }
                 q = r;
             }
-            i = j;
         }
     }
 
@@ -604,10 +623,18 @@ struct PlanImpl {
         const long long n = (long long)H * W;
         auto_flagged = 0;
         auto_guided.clear();
-        for (int f0 = 0; f0 < n_frames; f0 += chunk) {
+        if (unwrap == 3 && n_frames > 0) {
+            frameflag.grow((size_t)n_frames);
+            rt::dmemset(frameflag.ptr, 0, sizeof(int) * (size_t)n_frames, s);
+        }
+        auto wave_of = [&](int f0) {
             const int nf = std::min(chunk, n_frames - f0);
-            const Wave a{static_cast<const unsigned char*>(frames) + (size_t)f0 * n * px, frame_kind, nf,
-                         height_out + (long long)f0 * n, mask ? mask + (long long)f0 * mask_stride : nullptr, mask_stride};
+            return Wave{static_cast<const unsigned char*>(frames) + (size_t)f0 * n * px, frame_kind, nf,
+                        height_out + (long long)f0 * n, mask ? mask + (long long)f0 * mask_stride : nullptr, mask_stride};
+        };
+        for (int f0 = 0; f0 < n_frames; f0 += chunk) {
+            const Wave a = wave_of(f0);
+            const int nf = a.nf;
             float* po = phases ? phases + (long long)f0 * 2 * n : nullptr;
             if (profiling) timer.begin_chunk(s, nf);
             // unwrap: 0 none, 1 row/column scan (exact where the wrapped phases have no residues),
@@ -624,16 +651,18 @@ struct PlanImpl {
                 continue;
             }
             const int scan = unwrap ? 1 : 0;
-            int* flags = nullptr;
-            if (unwrap == 3) {
-                frameflag.grow((size_t)chunk);
-                rt::dmemset(frameflag.ptr, 0, sizeof(int) * (size_t)nf, s);
-                flags = frameflag.ptr;
-            }
-            stage_front(a, po, scan, flags, s);
+            stage_front(a, po, scan, unwrap == 3 ? frameflag.ptr + f0 : nullptr, s);
             stage_link(nf, po, scan, s);
             stage_back(a, 0, nf, scan, s);
-            if (unwrap == 3) auto_second_look(a, f0, po, s);
+        }
+        if (unwrap == 3 && n_frames > 0) {
+            // ONE read-back per call (4 bytes per frame), after every wave has been queued: on frames that cannot wrap
+            // "auto" costs nothing else.
+            std::vector<int> flags((size_t)n_frames), idx;
+            rt::d2h(flags.data(), frameflag.ptr, sizeof(int) * (size_t)n_frames, s);
+            for (int k = 0; k < n_frames; ++k)
+                if (flags[(size_t)k]) idx.push_back(k);
+            if (!idx.empty()) auto_second_look(idx, frames, frame_kind, height_out, phases, mask, mask_stride, s);
         }
     }
 

@@ -437,7 +437,7 @@ struct RowPhaseFwdParams {
 };
 template <int L, int G>
 struct RowPhaseFwd : AllPhases {
-    using FF = Fft<L, -1, float>;
+    using FF = Fft<L, -1, float, RowPlan<L>>;
     using GL = GroupLayout<L, G>;
     using Params = RowPhaseFwdParams;
     static constexpr bool BLOCKED_TILES = false;

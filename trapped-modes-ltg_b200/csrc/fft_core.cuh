@@ -193,6 +193,13 @@ template <> struct ColPlan<2048> { static constexpr int R1 = 16, R2 = 8, R3 = 16
 template <> struct ColPlan<1024> { static constexpr int R1 = 16, R2 = 8, R3 = 8; };
 template <> struct ColPlan<512>  { static constexpr int R1 = 16, R2 = 4, R3 = 8; };
 
+// Radix order of the ROW kernels (K1, K3, K5, RowPhaseFwd; lanes = consecutive elements of one transform).  The first
+// pass stays radix 8 (K3's pruned pass needs it); for 1024 and 512 the order of the other two matters: a radix-8 middle
+// pass scatters with stride 8 behind a radix-8 first pass and conflicts two ways, radix 16 in the middle does not.
+template <int L> struct RowPlan : Plan<L> {};
+template <> struct RowPlan<1024> { static constexpr int R1 = 8, R2 = 16, R3 = 8; };
+template <> struct RowPlan<512>  { static constexpr int R1 = 8, R2 = 16, R3 = 4; };
+
 // smem slot of logical element p: one pad element per 16 (keeps radix-strided writes of
 // the first pass and 16-aligned runs of the later passes bank-conflict free)
 FCD_HD int fft_pos(int p) { return p + (p >> 4); }
