@@ -1006,10 +1006,10 @@ struct PlanImpl {
             launch<LabelMerge>(blocks_for(total / 32), 1, s, LabelMergeParams{m_L.ptr, m_bits.ptr, total / 32, H, W});
             rt::dmemset(m_best.ptr, 0, sizeof(unsigned long long) * (size_t)nf, s);
             RegionStats st{m_area.ptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-            launch<RootStatsInit>(blocks_for(total), 1, s, RootStatsInitParams{m_L.ptr, st, total, (int)n, 0});
-            launch<LabelFlatten>(blocks_for(32LL * nf * H), 1, s, LabelFlattenParams{m_L.ptr, st, (long long)nf * H, H, W, 0});
-            launch<LargestRegion>(blocks_for(total), 1, s, LargestParams{m_L.ptr, st, m_best.ptr, total, H, W, 0});
-            launch<MaskOut>(blocks_for(total), 1, s, MaskOutParams{m_L.ptr, m_best.ptr, mask_out + f0 * n, total, (int)n});
+            launch<RootStatsInit>(blocks_for(total / 32), 1, s, RootStatsInitParams{m_L.ptr, m_bits.ptr, st, total / 32, H, W, 0});
+            launch<LabelFlatten>(blocks_for(32LL * nf * H), 1, s, LabelFlattenParams{m_L.ptr, m_bits.ptr, st, (long long)nf * H, H, W, 0});
+            launch<LargestRegion>(blocks_for(total / 32), 1, s, LargestParams{m_L.ptr, m_bits.ptr, st, m_best.ptr, total / 32, H, W, 0});
+            launch<MaskOut>(blocks_for(total / 32), 1, s, MaskOutParams{m_L.ptr, m_bits.ptr, m_best.ptr, mask_out + f0 * n, total / 32, H, W});
         }
     }
 
@@ -1025,9 +1025,9 @@ struct PlanImpl {
             rt::dmemset(m_best.ptr, 0, sizeof(unsigned long long) * (size_t)nf, s);
             int* minr = m_bbox.ptr; int* maxr = minr + total; int* minc = maxr + total; int* maxc = minc + total;
             RegionStats st{m_area.ptr, minr, maxr, minc, maxc, m_sums.ptr, m_sums.ptr + total};
-            launch<RootStatsInit>(blocks_for(total), 1, s, RootStatsInitParams{m_L.ptr, st, total, (int)n, 1});
-            launch<LabelFlatten>(blocks_for(32LL * nf * H), 1, s, LabelFlattenParams{m_L.ptr, st, (long long)nf * H, H, W, 1});
-            launch<LargestRegion>(blocks_for(total), 1, s, LargestParams{m_L.ptr, st, m_best.ptr, total, H, W, 1});
+            launch<RootStatsInit>(blocks_for(total / 32), 1, s, RootStatsInitParams{m_L.ptr, m_bits.ptr, st, total / 32, H, W, 1});
+            launch<LabelFlatten>(blocks_for(32LL * nf * H), 1, s, LabelFlattenParams{m_L.ptr, m_bits.ptr, st, (long long)nf * H, H, W, 1});
+            launch<LargestRegion>(blocks_for(total / 32), 1, s, LargestParams{m_L.ptr, m_bits.ptr, st, m_best.ptr, total / 32, H, W, 1});
             launch<CenterOut>(blocks_for(nf), 1, s, CenterOutParams{m_best.ptr, st, m_centers.ptr, nf, (int)n});
             rt::d2h(centers_host + 2 * f0, m_centers.ptr, sizeof(int) * 2 * (size_t)nf, s);
         }
