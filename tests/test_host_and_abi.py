@@ -192,3 +192,21 @@ def test_bench_reference_arm_contract():
     assert d["impl"] == "reference" and d["value"] > 0 and d["vs_baseline"] is None
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+
+
+def test_mask_bytes_reinterprets_instead_of_copying():
+    """Masks reach the kernels as one byte per pixel, zero = keep.  bool / uint8 masks must not be copied (a dtype
+    copy of a batch of 2048^2 masks costs more than K1); other dtypes become 0 / 1 bytes of their truth value."""
+    import torch
+    from fcd_b200 import engine as e
+    b = torch.zeros((3, 8, 8), dtype=torch.bool); b[1, 2:5, 3] = True
+    v = e._mask_bytes(b, torch.device("cpu"))
+    assert v.dtype == torch.uint8 and v.data_ptr() == b.data_ptr() and v.tolist() == b.to(torch.uint8).tolist()
+    u = torch.tensor([[0, 1], [7, 0]], dtype=torch.uint8)
+    assert e._mask_bytes(u, torch.device("cpu")).data_ptr() == u.data_ptr()
+    w = e._mask_bytes(np.array([[0.0, -2.5], [256.0, 0.0]]), torch.device("cpu"))      # 256 must not wrap to 0
+    assert w.dtype == torch.uint8 and w.tolist() == [[0, 1], [1, 0]]
+    nb = e._mask_bytes(np.array([[True, False]]), torch.device("cpu"))
+    assert nb.dtype == torch.uint8 and nb.tolist() == [[1, 0]]
+    t = torch.ones((4, 6), dtype=torch.bool)[:, ::2]                                    # non-contiguous view
+    assert e._mask_bytes(t, torch.device("cpu")).is_contiguous()

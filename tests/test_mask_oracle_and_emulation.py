@@ -102,3 +102,47 @@ def test_random_masks_stress_connected_components():
         img = (rng.random((64, 64)) < rng.choice([0.4, 0.55, 0.7])).astype(np.float32)
         assert np.array_equal(plan.structure_mask(img, 1)[0], mo.mask(img, 1))
     plan.close()
+
+
+def test_division_by_the_window_size_is_exact():
+    """The box filters replace tmp / size by a multiply and two FMAs (csrc/fcd_mask.cuh::div_by_const); the result
+    has to be the division's, bit for bit, for every window size: sums of camera-like float32 values, doubles with
+    random significands over 80 binades, and neighbours of exact multiples of the size."""
+    import ctypes
+    from tests.emul_lib import lib
+    L = lib()
+    L.fcd_emul_div_mismatches.restype = ctypes.c_longlong
+    L.fcd_emul_div_mismatches.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_double]
+    rng = np.random.default_rng(7)
+    n = 200_000
+    for size in list(range(1, 65)) + [97, 127, 255, 1000]:
+        sums8 = rng.integers(0, 256, (n, min(size, 64))).astype(np.float32).astype(np.float64).sum(1)
+        sums16 = (rng.integers(0, 65536, (n, min(size, 64))).astype(np.float32) + rng.random((n, 1), np.float32)).astype(np.float64).sum(1)
+        unit = rng.random((n, min(size, 64)), np.float32).astype(np.float64).sum(1)
+        wide = np.ldexp(1.0 + rng.random(n), rng.integers(-40, 40, n)) * rng.choice([-1.0, 1.0], n)
+        mult = np.nextafter(rng.integers(0, 10**6, n).astype(np.float64) * size, rng.choice([-np.inf, np.inf], n))
+        a = np.ascontiguousarray(np.concatenate([sums8, sums16, unit, wide, mult, [0.0]]))
+        assert L.fcd_emul_div_mismatches(a.ctypes.data, a.size, float(size)) == 0, size
+
+
+@pytest.mark.parametrize("size", [1, 2, 3, 8, 14, 15, 16, 31, 32, 33, 47])
+def test_emulated_box_filter_is_scipys_uniform_filter(size):
+    """smooth = uniform_filter(image, size) (pydata/analyze.py:70): the emulated kernels reproduce scipy's float32
+    output exactly -- the field the threshold and np.mean then work on."""
+    import ctypes
+    from scipy.ndimage import uniform_filter
+    from tests.emul_lib import lib
+    L = lib()
+    L.fcd_emul_box_filter.restype = None
+    L.fcd_emul_box_filter.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 4
+    rng = np.random.default_rng(size)
+    H, W = 64, 128
+    imgs = np.stack([rng.integers(0, 1024, (H, W)).astype(np.float32),                  # 10-bit camera counts
+                     rng.random((H, W), np.float32),
+                     (rng.random((H, W), np.float32) < 0.5).astype(np.float32) * 255.0])
+    tmp, out = np.empty_like(imgs), np.empty_like(imgs)
+    L.fcd_emul_box_filter(imgs.ctypes.data, tmp.ctypes.data, out.ctypes.data, len(imgs), H, W, size)
+    for k in range(len(imgs)):
+        want = uniform_filter(imgs[k], size)
+        assert want.dtype == np.float32
+        assert np.array_equal(out[k].view(np.uint32), want.view(np.uint32)), (size, k)

@@ -247,7 +247,7 @@ struct RowFwdParams {
 
 template <int L, int G>
 struct RowFwd : AllPhases {
-    using F = Fft<L, -1, float, RowPlan<L>>;
+    using F = Fft<L, -1, float, RegenRowPlan<L>>;     // same radix order and table as RowPlan<L> (fft_core.cuh, TwRegen)
     using GL = GroupLayout<L, G>;
     using Params = RowFwdParams;
     static constexpr bool BLOCKED_TILES = false;
@@ -1053,7 +1053,7 @@ struct RowInvParams {
 
 template <int L, int G>
 struct RowInv : AllPhases {
-    using FI = Fft<L, +1, float, RowPlan<L>>;
+    using FI = Fft<L, +1, float, RegenRowPlan<L>>;    // same radix order and table as RowPlan<L> (fft_core.cuh, TwRegen)
     using GL = GroupLayout<L, G>;
     using Params = RowInvParams;
     static constexpr bool BLOCKED_TILES = false;

@@ -27,6 +27,19 @@ FCD_HD int ilog2_pow2(int v) {
 #endif
 }
 
+// tmp / size, bit for bit, without the division routine (a reciprocal estimate, Newton steps and a slow path per
+// pixel -- half the instructions of the box filters in round 1).  With r = RN(1 / d) computed once per thread:
+//     q = RN(a * r);  rem = a - q * d  (exact in one FMA);  RN(q + rem * r)
+// is the correctly rounded quotient (Markstein's theorem: r correctly rounded, q within an ulp of a / d; it is the
+// last step of the hardware routine itself).  d is a small integer and a a finite sum of float32 values here, so
+// neither the exceptional divisors of the theorem (significand all ones) nor underflow of the remainder can occur.
+// tests/test_mask_oracle_and_emulation.py compares it with the division on 10^7 sums for every window size.
+FCD_HD double div_by_const(double a, double d, double r) {
+    const double q = a * r;
+    const double rem = fma(-q, d, a);
+    return fma(rem, r, q);
+}
+
 struct ElemBase : NoPrologue {
     static constexpr bool BLOCKED_TILES = false;
     static constexpr bool PIPELINED = false;
@@ -58,7 +71,7 @@ struct BoxLines : ElemBase {
         const float* __restrict__ a = p.in + base;
         float* __restrict__ o = p.out + base;
         const int s1 = p.size / 2, s2 = p.size - s1 - 1;
-        const double dsize = (double)p.size;
+        const double dsize = (double)p.size, rsize = 1.0 / dsize;
         auto at = [&](int j) -> double {           // 'reflect': d c b a | a b c d | d c b a
             if (j < 0) j = -j - 1;
             if (j >= n) j = 2 * n - 1 - j;
@@ -66,13 +79,13 @@ struct BoxLines : ElemBase {
         };
         double tmp = 0.0;
         for (int l = 0; l < p.size; ++l) tmp += at(l - s1);
-        o[0] = (float)(tmp / dsize);
+        o[0] = (float)div_by_const(tmp, dsize, rsize);
         // interior: no boundary handling, loads independent of the running sum -> unrolled
         int l = 1;
         for (; l < n && l - 1 - s1 < 0; ++l) {
             const double d = at(l + s2) - at(l - 1 - s1);
             tmp += d;
-            o[(long long)l * stride] = (float)(tmp / dsize);
+            o[(long long)l * stride] = (float)div_by_const(tmp, dsize, rsize);
         }
         const int l_hi = n - s2;      // l + s2 < n
         for (; l + 8 <= l_hi; l += 8) {
@@ -86,13 +99,13 @@ struct BoxLines : ElemBase {
             for (int q = 0; q < 8; ++q) {
                 const double d = nv[q] - ov[q];
                 tmp += d;
-                o[(long long)(l + q) * stride] = (float)(tmp / dsize);
+                o[(long long)(l + q) * stride] = (float)div_by_const(tmp, dsize, rsize);
             }
         }
         for (; l < n; ++l) {
             const double d = at(l + s2) - at(l - 1 - s1);
             tmp += d;
-            o[(long long)l * stride] = (float)(tmp / dsize);
+            o[(long long)l * stride] = (float)div_by_const(tmp, dsize, rsize);
         }
     }
 };
@@ -119,7 +132,7 @@ struct BoxRowsWarp : NoPrologue {
         if (wid * 32 >= p.n_lines) return;
         const int n = p.W;
         const int s1 = p.size / 2, s2 = p.size - s1 - 1;
-        const double dsize = (double)p.size;
+        const double dsize = (double)p.size, rsize = 1.0 / dsize;
 #if defined(__CUDA_ARCH__)
         const float* __restrict__ a = p.in + wid * 32 * n;                // 32 consecutive rows (same frame: H % 32 == 0)
         float* __restrict__ o = p.out + wid * 32 * n;
@@ -141,20 +154,50 @@ struct BoxRowsWarp : NoPrologue {
         __syncwarp();
         double tmp = 0.0;
         for (int l = 0; l < p.size; ++l) tmp += at(l - s1);
+        int slot = 0;                                                     // k % 3
         for (int k = 0; k < ntiles; ++k) {
-            for (int cc = 0; cc < 32; ++cc) {
-                const int l = 32 * k + cc;
-                if (l > 0) {
-                    const double d = at(l + s2) - at(l - 1 - s1);
+            // tile k + 2 is requested now and parked in registers: its DRAM round trip runs under this tile's recurrence
+            float nx[32];
+            const bool more = k + 2 < ntiles;
+            if (more) {
+                FCD_UNROLL
+                for (int rr = 0; rr < 32; ++rr) nx[rr] = a[(long long)rr * n + 32 * (k + 2) + lane];
+            }
+            if (k > 0 && k + 1 < ntiles) {
+                // interior tile (size <= 32): the entering sample sits in tile k or k + 1, the leaving one in tile
+                // k - 1 or k, no reflection -- two address selects per pixel instead of the general lookup
+                const float* tc = T + slot * TILE + lane * 33;                              // tile k
+                const float* tn = T + (slot == 2 ? 0 : slot + 1) * TILE + lane * 33 - 32;   // tile k + 1, column - 32
+                const float* tp = T + (slot == 0 ? 2 : slot - 1) * TILE + lane * 33 + 32;   // tile k - 1, column + 32
+                FCD_UNROLL
+                for (int cc = 0; cc < 32; ++cc) {
+                    const int jn = cc + s2, jo = cc - 1 - s1;
+                    const double nv = (double)(jn < 32 ? tc : tn)[jn];
+                    const double ov = (double)(jo >= 0 ? tc : tp)[jo];
+                    const double d = nv - ov;
                     tmp += d;
+                    O[lane * 33 + cc] = (float)div_by_const(tmp, dsize, rsize);
                 }
-                O[lane * 33 + cc] = (float)(tmp / dsize);
+            } else {
+                for (int cc = 0; cc < 32; ++cc) {
+                    const int l = 32 * k + cc;
+                    if (l > 0) {
+                        const double d = at(l + s2) - at(l - 1 - s1);
+                        tmp += d;
+                    }
+                    O[lane * 33 + cc] = (float)div_by_const(tmp, dsize, rsize);
+                }
             }
             __syncwarp();
             FCD_UNROLL
             for (int rr = 0; rr < 32; ++rr) o[(long long)rr * n + 32 * k + lane] = O[rr * 33 + lane];
-            if (k + 2 < ntiles) load_tile(k + 2);          // replaces tile k - 1, which no later column reads
+            if (more) {                                    // replaces tile k - 1, which no later column reads
+                float* t = T + (slot == 0 ? 2 : slot - 1) * TILE;
+                FCD_UNROLL
+                for (int rr = 0; rr < 32; ++rr) t[rr * 33 + lane] = nx[rr];
+            }
             __syncwarp();
+            slot = slot == 2 ? 0 : slot + 1;
         }
 #else
         // sequential emulation: the same recurrence, one row per emulated thread
@@ -172,7 +215,7 @@ struct BoxRowsWarp : NoPrologue {
                 const double d = at(l + s2) - at(l - 1 - s1);
                 tmp += d;
             }
-            o[l] = (float)(tmp / dsize);
+            o[l] = (float)div_by_const(tmp, dsize, rsize);
         }
         (void)smem;
 #endif
@@ -324,14 +367,57 @@ struct LabelInit : ElemBase {
         const long long o = row * p.W;
         const float thr = p.mode == 0 ? p.sums[f] / (float)n : 0.f;   // np.mean: float32 sum / count
 #if defined(__CUDA_ARCH__)
+        // Several loads per lane are in flight before the first ballot: one 128-byte request per warp and trip left the
+        // kernel waiting on DRAM latency (round 2, ncu launch list: 630 us for 268 MB of floats, 400 us for 67 MB of bytes).
         unsigned carry = 0u;                        // last pixel of the previous word is foreground
-        for (int c0 = 0; c0 < p.W; c0 += 32) {
-            const bool fg = fg_at(p, o, c0 + lane, thr);
-            const unsigned bits = __ballot_sync(0xffffffffu, fg);
+        auto emit = [&](unsigned bits, int c0) {    // warp-uniform word of 32 pixels starting at column c0
             const unsigned starts = bits & ~((bits << 1) | carry);
             if ((starts >> lane) & 1u) p.L[o + c0 + lane] = r * p.W + c0 + lane;
-            if (lane == 0) p.bits[(o + c0) >> 5] = bits;
             carry = bits >> 31;
+        };
+        if (p.mode == 0) {
+            const float* __restrict__ a = p.smooth + o;
+            for (int c0 = 0; c0 < p.W; c0 += 128) {                 // four words per trip (W is a multiple of 64)
+                float v[4];
+                FCD_UNROLL
+                for (int q = 0; q < 4; ++q) v[q] = (c0 + 32 * q < p.W) ? a[c0 + 32 * q + lane] : thr;
+                unsigned mine = 0u;
+                FCD_UNROLL
+                for (int q = 0; q < 4; ++q) {
+                    if (c0 + 32 * q < p.W) {
+                        const unsigned bits = __ballot_sync(0xffffffffu, v[q] < thr);
+                        emit(bits, c0 + 32 * q);
+                        if (lane == q) mine = bits;
+                    }
+                }
+                if (lane < 4 && c0 + 32 * lane < p.W) p.bits[((o + c0) >> 5) + lane] = mine;
+            }
+        } else if ((reinterpret_cast<uintptr_t>(p.mask) & 15u) == 0) {
+            // 16 mask bytes per lane: 512 pixels per trip.  Lane l covers columns c0 + 16 l .. + 15, i.e. one half of
+            // bitmap word l / 2; the two halves meet in one shuffle.
+            const uint4* __restrict__ m16 = reinterpret_cast<const uint4*>(p.mask + o);
+            for (int c0 = 0; c0 < p.W; c0 += 512) {
+                const bool in = c0 + 16 * lane < p.W;
+                uint4 m = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);      // beyond the line: background
+                if (in) m = m16[(c0 >> 4) + lane];
+                // byte == 0 -> foreground bit: per 32-bit word a 0 / 1 flag per byte, gathered into a nibble by a multiply
+                auto nib = [](unsigned w) { return (((__vcmpeq4(w, 0u) & 0x01010101u) * 0x01020408u) >> 24) & 15u; };
+                unsigned v = nib(m.x) | (nib(m.y) << 4) | (nib(m.z) << 8) | (nib(m.w) << 12);
+                v <<= 16 * (lane & 1);
+                v |= __shfl_xor_sync(0xffffffffu, v, 1);             // both lanes of a pair hold word lane / 2
+                FCD_UNROLL
+                for (int q = 0; q < 16; ++q) {
+                    const unsigned bits = __shfl_sync(0xffffffffu, v, 2 * q);
+                    if (c0 + 32 * q < p.W) emit(bits, c0 + 32 * q);
+                }
+                if (!(lane & 1) && in) p.bits[((o + c0) >> 5) + (lane >> 1)] = v;
+            }
+        } else {                                    // a caller's mask that is not 16-byte aligned: byte loads
+            for (int c0 = 0; c0 < p.W; c0 += 32) {
+                const unsigned bits = __ballot_sync(0xffffffffu, p.mask[o + c0 + lane] == 0);
+                emit(bits, c0);
+                if (lane == 0) p.bits[(o + c0) >> 5] = bits;
+            }
         }
 #else
         for (int c = lane; c < p.W; c += 32)        // sequential emulation: every emulated thread looks left on its own

@@ -20,6 +20,7 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <type_traits>
 #include <vector>
 
 #if defined(__CUDACC__)
@@ -200,6 +201,16 @@ template <int L> struct RowPlan : Plan<L> {};
 template <> struct RowPlan<1024> { static constexpr int R1 = 8, R2 = 16, R3 = 8; };
 template <> struct RowPlan<512>  { static constexpr int R1 = 8, R2 = 16, R3 = 4; };
 
+// Twiddle regeneration (per plan type): a radix-16 butterfly loads the powers 1, 2, 4, 8 of its twiddle and multiplies
+// the other eleven together -- two packed instructions each instead of an 8-byte shared-memory read.  Measured on a
+// B200 at 2048^2 (profiles/README.md, "twiddle regeneration"): K1 RowFwd 6.54 -> 6.23 us and K5 RowInv 5.53 -> 5.38 us
+// per frame, K3 and K4 unchanged (they are not bound by shared-memory bandwidth), K2 4.79 -> 4.93 us.  So only the
+// plans of K1 and K5 ask for it; -DFCD_TW_REGEN=1|2 forces it everywhere (2: radix-8 butterflies too) for A/B runs.
+// Products of two rounded table entries are good to about 1.5 ulp instead of 0.5.
+template <class P, class = void> struct TwRegen { static constexpr int value = 0; };
+template <class P> struct TwRegen<P, std::void_t<decltype(P::TW_REGEN)>> { static constexpr int value = P::TW_REGEN; };
+template <int L> struct RegenRowPlan : RowPlan<L> { static constexpr int TW_REGEN = 1; };
+
 // smem slot of logical element p: one pad element per 16 (keeps radix-strided writes of
 // the first pass and 16-aligned runs of the later passes bank-conflict free)
 FCD_HD int fft_pos(int p) { return p + (p >> 4); }
@@ -250,6 +261,38 @@ struct Fft {
         return t;
     }
 
+    // Twiddles W^(k*a), a = 1..R-1, of one butterfly: R - 1 loads from the [a][k] table, or (TwRegen above) the
+    // power-of-two powers loaded and the rest multiplied together.
+#if defined(FCD_TW_REGEN)
+    static constexpr int REGEN = FCD_TW_REGEN;
+#else
+    static constexpr int REGEN = TwRegen<P>::value;
+#endif
+    template <int R, int PP>
+    FCD_HD static void twiddles(cx<T>* w, const cx<T>* __restrict__ tw) {
+        if constexpr ((R == 16 && REGEN >= 1) || (R == 8 && REGEN >= 2)) {
+            FCD_UNROLL
+            for (int a = 1; a < R; a <<= 1) {
+                const cx<T> x = tw[a * PP];
+                w[a] = DIR < 0 ? x : conj(x);
+            }
+            w[3] = w[1] * w[2];
+            w[5] = w[1] * w[4];
+            w[6] = w[2] * w[4];
+            w[7] = w[3] * w[4];
+            if constexpr (R == 16) {
+                FCD_UNROLL
+                for (int a = 1; a < 8; ++a) w[8 + a] = w[8] * w[a];
+            }
+        } else {
+            FCD_UNROLL
+            for (int a = 1; a < R; ++a) {
+                const cx<T> x = tw[a * PP];
+                w[a] = DIR < 0 ? x : conj(x);
+            }
+        }
+    }
+
     // gather butterfly inputs of a pass with radix R and prior product PP; apply twiddles
     template <int R, int PP>
     FCD_HD static void gather(cx<T>* v, int t, const cx<T>* s, const cx<T>* __restrict__ table) {
@@ -259,16 +302,14 @@ struct Fft {
             const int i = t + TPF * ii;
             const int k = i & (PP - 1);
             constexpr int OFF = (THREE && PP == R1) ? 0 : TW_MID;
-            const cx<T>* __restrict__ tw = table + OFF + k;
             constexpr bool FAST = ((L / R) % 16 == 0);
             const cx<T>* sb = s + fft_pos(i);
+            cx<T> w[R];
+            if constexpr (PP > 1) twiddles<R, PP>(w, table + OFF + k);
             FCD_UNROLL
             for (int a = 0; a < R; ++a) {
                 cx<T> val = FAST ? sb[fft_padc(a * (L / R))] : s[fft_pos(i + a * (L / R))];
-                if (PP > 1 && a > 0) {
-                    const cx<T> w = tw[a * PP];
-                    val = val * (DIR < 0 ? w : conj(w));
-                }
+                if (PP > 1 && a > 0) val = val * w[a];
                 v[ii + NB * a] = val;
             }
         }
@@ -283,18 +324,17 @@ struct Fft {
             const int i = t + TPF * ii;
             const int k = i & (PP - 1);
             constexpr int OFF = (THREE && PP == R1) ? 0 : TW_MID;
-            const cx<T>* __restrict__ tw = table + OFF + k;
             constexpr bool FAST = ((L / R) % 16 == 0);
             const int pb = fft_pos(i);
+            cx<T> w[R];
+            if constexpr (PP > 1) twiddles<R, PP>(w, table + OFF + k);
             FCD_UNROLL
             for (int a = 0; a < R; ++a) {
                 const int pos = FAST ? pb + fft_padc(a * (L / R)) : fft_pos(i + a * (L / R));
                 cx<T> x0 = s0[pos], x1 = s1[pos];
                 if (PP > 1 && a > 0) {
-                    cx<T> w = tw[a * PP];
-                    if (DIR > 0) w = conj(w);
-                    x0 = x0 * w;
-                    x1 = x1 * w;
+                    x0 = x0 * w[a];
+                    x1 = x1 * w[a];
                 }
                 v0[ii + NB * a] = x0;
                 v1[ii + NB * a] = x1;

@@ -109,6 +109,19 @@ def to_device_image(a, device, allow_f64=True) -> torch.Tensor:
 UNWRAP_MODES = {"off": 0, "scan": 1, "herraez": 2, "guided": 2, "auto": 3}
 
 
+def _mask_bytes(mask, device) -> torch.Tensor:
+    """A mask as the kernels read it: one byte per pixel on `device`, zero = keep.  torch.bool storage is exactly
+    that, so bool (what analyze.mask returns) and uint8 masks are reinterpreted, not copied: a dtype copy of a
+    batch of 2048^2 masks costs 10 us per frame, more than K1 (profiles/launches_r02b_masked.csv)."""
+    mk = mask if isinstance(mask, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(mask))
+    mk = mk.to(device)
+    if mk.dtype == torch.bool:
+        mk = mk.contiguous().view(torch.uint8)
+    elif mk.dtype != torch.uint8:
+        mk = (mk != 0).view(torch.uint8)
+    return mk.contiguous()
+
+
 def unwrap_mode(unwrap) -> int:
     """False / 'off' -> 0;  True / 'scan' -> 1 (row/column scan: the fast path, exact where the
     wrapped phases have no residues);  'herraez' -> 2 (reliability-guided, what
@@ -282,7 +295,7 @@ class HeightMapPlan:
         mask_stride = 0
         mk = None
         if mask is not None:
-            mk = mask.to(self.device).to(torch.uint8).contiguous()
+            mk = _mask_bytes(mask, self.device)
             if mk.dim() == 3:
                 if mk.shape[0] != n:
                     raise ValueError("per-frame mask count differs from frame count")
@@ -354,14 +367,13 @@ class HeightMapPlan:
         with torch.cuda.device(self.device):
             check(self.lib, self.lib.fcd_structure_mask(self._h, _ptr(fr), int(fr.shape[0]), int(smoothed), _ptr(out),
                                                         _stream_ptr()))
-        out = out.bool()
+        out = out.view(torch.bool)          # the kernels write 0 / 1 bytes: reinterpreted, not copied
         return out[0] if squeeze else out
 
     def mask_center(self, masks) -> list:
         """analyze.center for a batch of masks: [(cy, cx), ...]; (-1, -1) where there is no enclosed region."""
-        mk = masks if isinstance(masks, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(masks))
-        mk = mk.to(self.device).to(torch.uint8)
-        mk = (mk.unsqueeze(0) if mk.dim() == 2 else mk).contiguous()
+        mk = _mask_bytes(masks, self.device)
+        mk = mk.unsqueeze(0) if mk.dim() == 2 else mk
         self._check_image(mk)
         n = int(mk.shape[0])
         out = (ctypes.c_int * (2 * max(n, 1)))()
