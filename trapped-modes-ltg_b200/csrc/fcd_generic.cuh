@@ -379,7 +379,8 @@ struct CcsgnStoreParams {
     const cd* g;
     cf* out_f;    // [H][W] complex64 (pipeline copy)
     cd* out_d;    // optional complex128 copy
-    float* theta; // optional angle(ccsgn) as float32 (what the demodulation kernel reads)
+    float* theta; // optional angle(ccsgn) as float32 (what the demodulation kernel reads): element i at theta[2 * i],
+                  // the two carriers interleaved so that K3 fetches both angles of a pixel in one 8-byte load
     long long n;
     int nblocks;
 };
@@ -397,7 +398,7 @@ struct CcsgnStore : NoPrologue {
             const cd z = conj(p.g[i]);
             if (p.out_f) p.out_f[i] = mk<float>((float)z.x, (float)z.y);
             if (p.out_d) p.out_d[i] = z;
-            if (p.theta) p.theta[i] = (float)atan2(z.y, z.x);
+            if (p.theta) p.theta[2 * i] = (float)atan2(z.y, z.x);
         }
     }
 };

@@ -22,13 +22,6 @@
 #include <cstring>
 #include "fft_core.cuh"
 
-#ifndef FCD_K3_FRAMEGROUPS
-#define FCD_K3_FRAMEGROUPS 0
-#endif
-#ifndef FCD_K3_PROBE
-#define FCD_K3_PROBE 0      // 1..4: timing probes of K3 (wrong results), see profiles/README.md
-#endif
-
 namespace fcd {
 
 constexpr float kTwoPiF = 6.28318530717958647692f;
@@ -476,7 +469,7 @@ struct ColBand : AllPhases {
 // =========================================================================================
 struct RowDemodParams {
     const cf* w2;
-    const float* theta;  // [2][H][W]  angle(ccsgn) of the bound reference
+    const float* theta;  // [H][W][2]  angle(ccsgn) of the bound reference, the two carriers interleaved
     cf* w3;              // [F][W/4+1][H][4]  (column-blocked, see w3_index)
     float* colphase;     // [F][2][H]
     float* phases;       // [F][2][H][W] or null
@@ -488,7 +481,6 @@ struct RowDemodParams {
     int unwrap;
     int* frameflag;      // [F] or null: set to 1 for frames with |phi| > pi/2 somewhere (the only frames that can
                          // hold a 2*pi jump, let alone a residue: unwrap "auto" looks no further at the others)
-    int nf;              // frames of this launch
 };
 
 struct int2s { int a, b; };
@@ -572,16 +564,14 @@ struct RowDemod {
         }
     }
     // -angle(g * ccsgn) = -wrap(angle(g) + angle(ccsgn))           (fcd.py:118)
-    FCD_HD static void load_theta(const Params& p, int i, int y, int t, float* c) {
-        const float* __restrict__ th = p.theta + ((long long)i * p.H + y) * L;
-#if FCD_K3_PROBE == 1     // timing probe (wrong results): no reference-angle loads
+    // both carriers' reference angles of pixels m0 .. m0 + 7 of this thread: one 8-byte load per pixel
+    FCD_HD static void load_theta8(const Params& p, int y, int t, int m0, float* c0, float* c1) {
+        const cf* __restrict__ th = reinterpret_cast<const cf*>(p.theta) + (long long)y * L;
         FCD_UNROLL
-        for (int m = 0; m < 16; ++m) c[m] = 0.001f * (float)(t + m);
-        (void)th;
-#else
-        FCD_UNROLL
-        for (int m = 0; m < 16; ++m) c[m] = th[t + TPF * m];
-#endif
+        for (int m = m0; m < m0 + 8; ++m) {
+            const cf a = th[t + TPF * m];
+            c0[m] = a.x; c1[m] = a.y;
+        }
     }
     FCD_HD static bool demod(const float* c, const cf* v, float* ph) {
         float big = 0.f;
@@ -609,19 +599,8 @@ struct RowDemod {
         int2s* off = reinterpret_cast<int2s*>(aux + 2 * TPF);   // [TPF]
         int* flag = group_flag(smem_all, tid);
         const int W = L;
-#if FCD_K3_FRAMEGROUPS
-        // the G groups of a block hold the SAME row of G consecutive frames: they read the same theta row within one
-        // tile (L1 hits for all but the first), and so do the next tiles (frame groups run fastest)
-        const int y = by;
-        const int f = bx * G + g;
-        if constexpr (PH == 0) {
-            if (t == 0) *flag = 0;
-        }
-        if (f >= p.nf) return;      // frames % G != 0: the surplus groups of the last frame group only keep their barriers
-#else
         const int y = by * G + g;   // tiles are ordered frame-fastest so that consecutive tiles of
         const int f = bx;           // a block reuse the same theta rows out of L2
-#endif
         if constexpr (PH == 0) {
             if (t == 0) *flag = 0;
             if constexpr (PRUNED) {
@@ -654,38 +633,25 @@ struct RowDemod {
             }
         } else if constexpr (PH == 1) {
             if constexpr (PRUNED) {   // own slots were consumed before the barrier: stage the next tile
-#if FCD_K3_FRAMEGROUPS
-                if (st.link.has_next && st.link.next_bx * G + g < p.nf)
-                    stage_band(p, st.link.next_bx * G + g, st.link.next_by, t, band_slots(gbase));
-#else
                 if (st.link.has_next)
                     stage_band(p, st.link.next_bx, st.link.next_by * G + g, t, band_slots(gbase));
-#endif
             }
-#if FCD_K3_PROBE != 5     // probe 5 (wrong results): the inverse transforms without their middle pass
             FI::stepB2(st.v, st.w, t, s0, s1, tw);
-#endif
         } else if constexpr (PH == 2) {
-#if FCD_K3_PROBE != 5
             FI::stepC(st.v, t, s0);
             FI::stepC(st.w, t, s1);
-#endif
         } else if constexpr (PH == 3) {
-            // theta of carrier 0 is requested before the last butterflies, theta of carrier 1 before carrier 0's
-            // arctangents: each batch of loads has a long stretch of arithmetic to hide behind
+            // the reference angles of the first eight pixels are requested before the last butterflies, those of the
+            // other eight before the first arctangents: each batch of loads has a stretch of arithmetic to hide behind
             float c0[16], c1[16];
-            load_theta(p, 0, y, t, c0);
+            load_theta8(p, y, t, 0, c0, c1);
             FI::stepD2(st.v, st.w, t, s0, s1, tw);
-            load_theta(p, 1, y, t, c1);
+            load_theta8(p, y, t, 8, c0, c1);
 #if defined(FCD_PACKED_F32)
             float big = 0.f;
             FCD_UNROLL
             for (int m = 0; m < 16; ++m) {
-#if FCD_K3_PROBE == 2     // timing probe (wrong results): no arctangents
-                st.v[m] = mk<float>(st.v[m].x * 1e-3f + c0[m], st.w[m].y * 1e-3f + c1[m]);
-#else
                 st.v[m] = demod_pair(st.v[m], st.w[m], c0[m], c1[m]);
-#endif
                 big = fmaxf(big, fmaxf(fabsf(st.v[m].x), fabsf(st.v[m].y)));
             }
             if (big > 1.57079632679489661923f) {               // this row may contain 2*pi jumps
@@ -767,265 +733,10 @@ struct RowDemod {
                     o1[t + TPF * m] = st.v[m].y;
                 }
             }
-#if FCD_K3_PROBE != 4     // probe 4 (wrong results): no forward transform, the phases are stored as they are
             FF::stepA(st.v, t, s0);
-#endif
         } else if constexpr (PH == 10) {
-#if FCD_K3_PROBE != 4
             FF::stepB(st.v, t, s0, tw);
-#endif
         } else if constexpr (PH == 11) {
-#if FCD_K3_PROBE != 4
-            FF::stepC(st.v, t, s0);
-#endif
-        } else {
-#if FCD_K3_PROBE != 4
-            FF::stepD(st.v, t, s0, tw);
-#endif
-#if FCD_K3_PROBE == 3     // probe 3 (wrong results): no w3 stores (a data-dependent guard keeps the arithmetic alive)
-            bool never = false;
-            FCD_UNROLL
-            for (int m = 0; m < 16; ++m) never = never || (st.v[m].x == 123456.789f);
-            if (!never) return;
-#endif
-            // column-blocked store (see w3_index): two bases, constant strides
-            const int H = p.H;
-            cf* base = p.w3 + ((long long)f * w3_blocks(W) * H + y) * 4;
-            const long long step = (long long)TPF * H;                     // TPF/4 blocks of H*4 elements
-            const long long lo = (long long)(t >> 2) * H * 4 + (t & 3);     // slot = t + TPF*m, m < 8
-            const int s8 = W / 2 + t + (t > 0 ? 3 : 0);                     // kc = W/2 + t (m = 8)
-            const int sh = W / 2 + t + 3;                                   // kc = W/2 + t + TPF*(m-8), m > 8
-            const long long o8 = (long long)(s8 >> 2) * H * 4 + (s8 & 3);
-            const long long hi = (long long)(sh >> 2) * H * 4 + (sh & 3);
-            FCD_UNROLL
-            for (int m = 0; m < 8; ++m) base[lo + m * step] = st.v[m];
-            base[o8] = st.v[8];
-            FCD_UNROLL
-            for (int m = 9; m < 16; ++m) base[hi + (m - 8) * step] = st.v[m];
-        }
-    }
-};
-
-
-
-// =========================================================================================
-// K3, one carrier at a time (round 2).  RowDemod above keeps both carriers of a row in registers (2 x 16 complex
-// values per thread -> 128 registers, one block of 16 warps per SM, 25 % of the warp slots); ncu shows it
-// latency-bound on that: issue slots half empty, no pipe saturated, and cutting its shared-memory reads by a sixth
-// changed nothing (profiles/README.md, "twiddle regeneration").  Here a thread transforms carrier 0, parks its 16
-// phases in shared memory, transforms carrier 1 and only then pairs them up -- 16 complex values of state, 80
-// registers, so a block holds G = 6 rows (24 warps) and needs ONE exchange buffer per row.  Same arithmetic per
-// element as RowDemod (bit-identical w3 / colphase / phases / flags: tests/test_emulated_kernels.py).  The parked
-// phases' slots later hold the jump scan array of the row unwrap, two 16-bit counts per word (|prefix| <= L).
-// Pruned first pass only (band no wider than L/8), L/16 >= 32 (named barrier per row); H need not divide by G.
-// =========================================================================================
-template <int L, int G>
-struct RowDemodSeq {
-    using FF = Fft<L, -1, float, RowPlan<L>>;
-    using FI = Fft<L, +1, float, RowPlan<L>>;
-    using GL = GroupLayout<L, G, 1>;
-    using Params = RowDemodParams;
-    static_assert(RowPlan<L>::R1 == 8 && L / 16 >= 32 && G <= 15, "pruned radix-8 first pass, one named barrier per row");
-    static constexpr bool BLOCKED_TILES = true;
-    static constexpr bool PIPELINED = true;
-    static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 17;
-    static constexpr int SYNC_THREADS = TPF;
-    static constexpr int MIN_BLOCKS = 1;
-    using TW = SmemTwiddles<FF, THREADS>;
-    // per row: exchange buffer | park (phi0, later the packed jump scan) | chunk totals, chunk offsets, flag | band slots
-    static constexpr int PARK_INTS = L + L / 16;
-    static constexpr int AUX_INTS = 4 * TPF + 4;
-    static constexpr int GROUP_BYTES = GL::STRIDE * (int)sizeof(cf) + PARK_INTS * (int)sizeof(int) +
-                                       AUX_INTS * (int)sizeof(int) + 4 * TPF * (int)sizeof(cf);
-    static_assert((GL::STRIDE * (int)sizeof(cf) + PARK_INTS * (int)sizeof(int) + AUX_INTS * (int)sizeof(int)) % 8 == 0,
-                  "band slots are 8-byte cp.async targets");
-    static constexpr int SMEM_BYTES = TW::TW_BYTES + G * GROUP_BYTES;
-    FCD_HD static void prologue(const Params& p, int tid, unsigned char* smem) { TW::load(p.tw, tid, smem); }
-    struct State {
-        cf v[16];
-        TileLink link;
-    };
-    using Pair = RowDemod<L, G, true>;      // band_col / load_theta / demod: the same helpers, the same arithmetic
-
-    FCD_HD static unsigned char* group_base(unsigned char* smem_all, int tid) {
-        return smem_all + TW::TW_BYTES + (size_t)(tid / TPF) * GROUP_BYTES;
-    }
-    FCD_HD static int* park_of(unsigned char* gbase) { return reinterpret_cast<int*>(gbase + GL::STRIDE * sizeof(cf)); }
-    FCD_HD static int* aux_of(unsigned char* gbase) { return park_of(gbase) + PARK_INTS; }
-    FCD_HD static cf* band_of(unsigned char* gbase) { return reinterpret_cast<cf*>(aux_of(gbase) + AUX_INTS); }
-    FCD_HD static void stage_band(const Params& p, int f, int y, int t, cf* band) {
-        FCD_UNROLL
-        for (int q = 0; q < 4; ++q) {
-            const int i = q >> 1;
-            const int c = Pair::band_col(p, i, t, q & 1);
-            if (c < p.nc[i]) async_copy8(band + q * TPF + t, p.w2 + (((long long)f * 2 + i) * p.H + y) * p.ncp + c);
-        }
-    }
-    template <int PH>
-    FCD_HD static bool enabled(const Params& p, const unsigned char* smem_all, int tid) {
-        if constexpr (PH >= 8 && PH <= 12)
-            return p.unwrap && aux_of(group_base(const_cast<unsigned char*>(smem_all), tid))[4 * TPF] != 0;
-        else
-            return true;
-    }
-    FCD_HD static int pack_jumps(int a, int b) { return (int)(((unsigned)a & 0xffffu) | ((unsigned)b << 16)); }
-    FCD_HD static int jump_a(int w) { return (int)(short)(w & 0xffff); }
-    FCD_HD static int jump_b(int w) { return w >> 16; }
-
-    // first pass of carrier i: two butterflies with one staged band value each
-    FCD_HD static void first_pass(const Params& p, int i, int t, const cf* band, cf* s0, const cf* tw) {
-        constexpr int M1 = L / 8;
-        const int p0 = p.kc0[i] & (L - 1);
-        FCD_UNROLL
-        for (int ii = 0; ii < 2; ++ii) {
-            const int c = (t + TPF * ii - p0) & (M1 - 1);
-            const cf x = (c < p.nc[i]) ? band[(i * 2 + ii) * TPF + t] : mk<float>(0.f, 0.f);
-            FI::stepA_single(x, ((p0 + c) & (L - 1)) / M1, ii, t, s0, tw);
-        }
-    }
-    // last pass of carrier i and its phases:  ph[m] = -wrap(angle(g) + theta)      (fcd.py:118)
-    FCD_HD static bool last_pass(const Params& p, int i, int y, int t, cf* v, const cf* s0, const cf* tw, float* ph) {
-        float c[16];
-        Pair::load_theta(p, i, y, t, c);      // requested before the butterflies that hide its latency
-        FI::stepD(v, t, s0, tw);
-#if defined(FCD_PACKED_F32)
-        float big = 0.f;
-        FCD_UNROLL
-        for (int m = 0; m < 16; m += 2) {     // two pixels of this carrier per packed chain
-            const cf r = demod_pair(v[m], v[m + 1], c[m], c[m + 1]);
-            ph[m] = r.x; ph[m + 1] = r.y;
-            big = fmaxf(big, fmaxf(fabsf(r.x), fabsf(r.y)));
-        }
-        return big > 1.57079632679489661923f;
-#else
-        return Pair::demod(c, v, ph);
-#endif
-    }
-
-    template <int PH>
-    FCD_HD static void phase(const Params& p, int bx, int by, int tid, unsigned char* smem_all, State& st) {
-        const cf* tw = reinterpret_cast<const cf*>(smem_all);
-        const int g = tid / TPF, t = tid % TPF;
-        unsigned char* gbase = group_base(smem_all, tid);
-        cf* s0 = reinterpret_cast<cf*>(gbase);
-        int* park = park_of(gbase);
-        float* parkf = reinterpret_cast<float*>(park);
-        int* aux = aux_of(gbase);
-        int2s* part = reinterpret_cast<int2s*>(aux);            // [TPF]
-        int2s* off = reinterpret_cast<int2s*>(aux + 2 * TPF);   // [TPF]
-        int* flag = aux + 4 * TPF;
-        cf* band = band_of(gbase);
-        const int W = L;
-        const int y = by * G + g;   // tiles are ordered frame-fastest: consecutive tiles of a block reuse theta rows
-        const int f = bx;
-        if constexpr (PH == 0) {
-            if (t == 0) *flag = 0;  // also for a row beyond the image: its scan phases stay off
-        }
-        if (y >= p.H) return;       // H % G != 0: the last tile's surplus rows only keep their barriers
-        if constexpr (PH == 0) {
-            if (st.link.first) stage_band(p, f, y, t, band);     // later tiles were staged in phase 5
-            async_wait_all();
-            first_pass(p, 0, t, band, s0, tw);
-        } else if constexpr (PH == 1 || PH == 5) {
-            if constexpr (PH == 5) {  // all four slots were consumed before the barrier: stage the next tile
-                const int yn = st.link.next_by * G + g;
-                if (st.link.has_next && yn < p.H) stage_band(p, st.link.next_bx, yn, t, band);
-            }
-            FI::stepB(st.v, t, s0, tw);
-        } else if constexpr (PH == 2 || PH == 6) {
-            FI::stepC(st.v, t, s0);
-        } else if constexpr (PH == 3) {
-            float ph[16];
-            const bool big = last_pass(p, 0, y, t, st.v, s0, tw, ph);
-            FCD_UNROLL
-            for (int m = 0; m < 16; ++m) parkf[m * TPF + t] = ph[m];      // thread-private slots
-            if (big) {
-                *flag = 1;
-                if (p.frameflag) p.frameflag[f] = 1;
-            }
-            if (t == (p.x_ref % TPF)) {
-                const int mr = p.x_ref / TPF;
-                float a = 0.f;
-                FCD_UNROLL
-                for (int mm = 0; mm < 16; ++mm)
-                    if (mm == mr) a = ph[mm];
-                p.colphase[((long long)f * 2 + 0) * p.H + y] = a;
-            }
-        } else if constexpr (PH == 4) {
-            first_pass(p, 1, t, band, s0, tw);
-        } else if constexpr (PH == 7) {
-            float ph[16];
-            const bool big = last_pass(p, 1, y, t, st.v, s0, tw, ph);
-            FCD_UNROLL
-            for (int m = 0; m < 16; ++m) st.v[m] = mk<float>(parkf[m * TPF + t], ph[m]);
-            if (big) {
-                *flag = 1;
-                if (p.frameflag) p.frameflag[f] = 1;
-            }
-            if (t == (p.x_ref % TPF)) {
-                const int mr = p.x_ref / TPF;
-                float a = 0.f;
-                FCD_UNROLL
-                for (int mm = 0; mm < 16; ++mm)
-                    if (mm == mr) a = ph[mm];
-                p.colphase[((long long)f * 2 + 1) * p.H + y] = a;
-            }
-        } else if constexpr (PH == 8) {           // ---- row unwrap (rows that may wrap only), as in RowDemod ----
-            FCD_UNROLL
-            for (int m = 0; m < 16; ++m) s0[fft_nat<TPF>(t, m)] = st.v[m];
-        } else if constexpr (PH == 9) {
-            FCD_UNROLL
-            for (int m = 0; m < 16; ++m) {
-                const int x = t + TPF * m;
-                int ja = 0, jb = 0;
-                if (x > 0) {
-                    const cf prev = s0[fft_pos(x - 1)];
-                    ja = (int)rintf((st.v[m].x - prev.x) * kInvTwoPiF);
-                    jb = (int)rintf((st.v[m].y - prev.y) * kInvTwoPiF);
-                }
-                park[fft_nat<TPF>(t, m)] = pack_jumps(ja, jb);
-            }
-        } else if constexpr (PH == 10) {
-            int a = 0, b = 0;              // inclusive scan of this thread's contiguous chunk
-            FCD_UNROLL
-            for (int q = 0; q < 16; ++q) {
-                const int w = park[fft_pos(16 * t + q)];
-                a += jump_a(w); b += jump_b(w);
-                park[fft_pos(16 * t + q)] = pack_jumps(a, b);
-            }
-            int2s tot; tot.a = a; tot.b = b;
-            part[t] = tot;
-        } else if constexpr (PH == 11) {
-            int a = 0, b = 0;
-            for (int q = 0; q < t; ++q) { a += part[q].a; b += part[q].b; }
-            int2s o; o.a = a; o.b = b;
-            off[t] = o;
-        } else if constexpr (PH == 12) {
-            const int cr = park[fft_pos(p.x_ref)];
-            const int2s orf = off[p.x_ref >> 4];
-            const int ra = jump_a(cr) + orf.a, rb = jump_b(cr) + orf.b;
-            FCD_UNROLL
-            for (int m = 0; m < 16; ++m) {
-                const int x = t + TPF * m;
-                const int c = park[fft_nat<TPF>(t, m)];
-                const int2s o = off[x >> 4];
-                st.v[m].x -= kTwoPiF * (float)(jump_a(c) + o.a - ra);
-                st.v[m].y -= kTwoPiF * (float)(jump_b(c) + o.b - rb);
-            }
-        } else if constexpr (PH == 13) {
-            if (p.phases) {
-                float* o0 = p.phases + (((long long)f * 2 + 0) * p.H + y) * W;
-                float* o1 = p.phases + (((long long)f * 2 + 1) * p.H + y) * W;
-                FCD_UNROLL
-                for (int m = 0; m < 16; ++m) {
-                    o0[t + TPF * m] = st.v[m].x;
-                    o1[t + TPF * m] = st.v[m].y;
-                }
-            }
-            FF::stepA(st.v, t, s0);
-        } else if constexpr (PH == 14) {
-            FF::stepB(st.v, t, s0, tw);
-        } else if constexpr (PH == 15) {
             FF::stepC(st.v, t, s0);
         } else {
             FF::stepD(st.v, t, s0, tw);
@@ -1046,6 +757,8 @@ struct RowDemodSeq {
         }
     }
 };
+
+
 
 // =========================================================================================
 // K3b row linking: integer prefix sum along y of the 2pi jumps of the anchor column.

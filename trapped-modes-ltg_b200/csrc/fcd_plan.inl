@@ -20,21 +20,14 @@ namespace fcd {
 
 // groups per block for each transform length (threads = G * L/16)
 template <int L> struct Tune;
-template <> struct Tune<64>   { static constexpr int GROW = 16, GCOL = 16, GDEM = 16, GGEN = 16, GDEM_SEQ = 0; };
-template <> struct Tune<128>  { static constexpr int GROW = 8,  GCOL = 8,  GDEM = 8,  GGEN = 8, GDEM_SEQ = 0; };
-template <> struct Tune<256>  { static constexpr int GROW = 8,  GCOL = 8,  GDEM = 8,  GGEN = 8, GDEM_SEQ = 0; };
-template <> struct Tune<512>  { static constexpr int GROW = 4,  GCOL = 4,  GDEM = 4,  GGEN = 4, GDEM_SEQ = 0; };
-// rows per block of the one-carrier-at-a-time K3 (RowDemodSeq, fcd_kernels.cuh); 0 = the two-carrier RowDemod
-#ifndef FCD_T1024_GDEM_SEQ
-#define FCD_T1024_GDEM_SEQ 0
-#endif
-#ifndef FCD_T2048_GDEM_SEQ
-#define FCD_T2048_GDEM_SEQ 0
-#endif
+template <> struct Tune<64>   { static constexpr int GROW = 16, GCOL = 16, GDEM = 16, GGEN = 16; };
+template <> struct Tune<128>  { static constexpr int GROW = 8,  GCOL = 8,  GDEM = 8,  GGEN = 8; };
+template <> struct Tune<256>  { static constexpr int GROW = 8,  GCOL = 8,  GDEM = 8,  GGEN = 8; };
+template <> struct Tune<512>  { static constexpr int GROW = 4,  GCOL = 4,  GDEM = 4,  GGEN = 4; };
 #ifndef FCD_T1024_GDEM
 #define FCD_T1024_GDEM 8
 #endif
-template <> struct Tune<1024> { static constexpr int GROW = 4,  GCOL = 4,  GDEM = FCD_T1024_GDEM,  GGEN = 4, GDEM_SEQ = FCD_T1024_GDEM_SEQ; };
+template <> struct Tune<1024> { static constexpr int GROW = 4,  GCOL = 4,  GDEM = FCD_T1024_GDEM,  GGEN = 4; };
 #ifndef FCD_T2048_GROW
 #define FCD_T2048_GROW 2
 #endif
@@ -44,8 +37,8 @@ template <> struct Tune<1024> { static constexpr int GROW = 4,  GCOL = 4,  GDEM 
 #ifndef FCD_T2048_GDEM
 #define FCD_T2048_GDEM 4
 #endif
-template <> struct Tune<2048> { static constexpr int GROW = FCD_T2048_GROW, GCOL = FCD_T2048_GCOL, GDEM = FCD_T2048_GDEM, GGEN = 2, GDEM_SEQ = FCD_T2048_GDEM_SEQ; };
-template <> struct Tune<4096> { static constexpr int GROW = 2,  GCOL = 2,  GDEM = 2,  GGEN = 2, GDEM_SEQ = 0; };
+template <> struct Tune<2048> { static constexpr int GROW = FCD_T2048_GROW, GCOL = FCD_T2048_GCOL, GDEM = FCD_T2048_GDEM, GGEN = 2; };
+template <> struct Tune<4096> { static constexpr int GROW = 2,  GCOL = 2,  GDEM = 2,  GGEN = 2; };
 
 #define FCD_CASE_L(N, ...) case N: { constexpr int L = N; __VA_ARGS__; } break;
 #define FCD_DISPATCH_L(value, ...)                                                      \
@@ -92,7 +85,7 @@ struct PlanImpl {
     std::vector<int> h_lo, h_hi;           // [2][ncp]
     rt::DevBuf<int> chord_lo, chord_hi;
     rt::DevBuf<cf> ccsgn;                  // [2][H][W] complex64 copy (Carrier.ccsgn)
-    rt::DevBuf<float> theta;               // [2][H][W] angle(ccsgn), read by the demodulation kernel
+    rt::DevBuf<float> theta;               // [H][W][2] angle(ccsgn) of the two carriers, read by the demodulation kernel
     rt::DevBuf<float> kx, kxq;
     float dky = 0.f;
     double f[2][2] = {{0, 0}, {0, 0}};     // carrier wavevectors [k_row, k_col]
@@ -443,7 +436,7 @@ struct PlanImpl {
             masked_inverse(i, s, nullptr);
             const int nb = elem_blocks(n);
             launch<CcsgnStore>(nb, 1, s, CcsgnStoreParams{tmp.ptr, ccsgn.ptr + (size_t)i * n, nullptr,
-                                                         theta.ptr + (size_t)i * n, n, nb});
+                                                         theta.ptr + i, n, nb});
         }
 
         // workspaces of the fused pipeline
@@ -487,36 +480,21 @@ struct PlanImpl {
         if (profiling) timer.mark(s, 1);
         stage_demod(0, a.nf, po, scan, flags, s);
     }
-    // pruned K3: the one-carrier-at-a-time kernel where Tune<L> names its rows per block, else the two-carrier kernel
-    // (a template so that the branch not taken is not instantiated: RowDemodSeq exists for some lengths only)
-    template <class K, int G>
-    void demod_grid(int nf, rt::stream_t s, const RowDemodParams& p) {
-#if FCD_K3_FRAMEGROUPS
-        launch<K>(ceil_div(nf, G), H, s, p);      // a block: one row of G consecutive frames
-#else
-        launch<K>(nf, H / G, s, p);               // a block: G consecutive rows of one frame
-#endif
-    }
-    template <int L, int GSEQ>
-    void launch_demod_pruned(int nf, rt::stream_t s, const RowDemodParams& p) {
-        if constexpr (GSEQ > 0) launch<RowDemodSeq<L, GSEQ>>(nf, ceil_div(H, GSEQ), s, p);
-        else demod_grid<RowDemod<L, Tune<L>::GDEM, true>, Tune<L>::GDEM>(nf, s, p);
-    }
     // K3 alone on the band-passed spectra w2 of frames [wf, wf + nf) of the current wave; writes w3 / colphase from
     // frame 0 on (the second look of unwrap "auto" demodulates a run of flagged frames again without redoing K1, K2)
     void stage_demod(int wf, int nf, float* po, int scan, int* flags, rt::stream_t s) {
         FCD_DISPATCH_L(W, {
             constexpr int G = Tune<L>::GDEM;
             RowDemodParams p{w2.ptr + (size_t)wf * 2 * H * ncp, theta.ptr, w3.ptr, colphase.ptr, po, tw_w_f.ptr, H, ncp,
-                             {nc[0], nc[1]}, {c_lo[0] - W / 2, c_lo[1] - W / 2}, W / 2, scan, flags, nf};
+                             {nc[0], nc[1]}, {c_lo[0] - W / 2, c_lo[1] - W / 2}, W / 2, scan, flags};
             bool pruned = false;
             if constexpr (RowPlan<L>::R1 == 8) {
                 if (nc[0] <= L / 8 && nc[1] <= L / 8) {
                     pruned = true;
-                    launch_demod_pruned<L, Tune<L>::GDEM_SEQ>(nf, s, p);
+                    launch<RowDemod<L, G, true>>(nf, H / G, s, p);
                 }
             }
-            if (!pruned) demod_grid<RowDemod<L, G, false>, G>(nf, s, p);
+            if (!pruned) launch<RowDemod<L, G, false>>(nf, H / G, s, p);
         })
         if (profiling) timer.mark(s, 2);
     }
