@@ -174,13 +174,18 @@ __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) fcd_kernel(const __
         t1 = (int)((long long)(blockIdx.x + 1) * ntiles / gridDim.x);
         step = 1;
     }
+    // tile -> (bx, by) = (tile % gx, tile / gx), kept incrementally: two divisions per block instead of four per
+    // tile (the issue-bound kernels spent 4 % of their instructions on them, SASS of round 2)
+    if (t0 >= t1) return;
+    int bx = t0 % gx, by = t0 / gx;
+    const int sx = step % gx, sy = step / gx;
     for (int tile = t0; tile < t1; tile += step) {
-        if constexpr (K::PIPELINED) {
-            const int nt = tile + step;
-            st.link = TileLink{nt % gx, nt / gx, nt < t1, tile == t0};
-        }
-        run_phases<K, 0>(p, tile % gx, tile / gx, fcd_smem, st);
+        int nbx = bx + sx, nby = by + sy;
+        if (nbx >= gx) { nbx -= gx; ++nby; }
+        if constexpr (K::PIPELINED) st.link = TileLink{nbx, nby, tile + step < t1, tile == t0};
+        run_phases<K, 0>(p, bx, by, fcd_smem, st);
         phase_barrier<K>();
+        bx = nbx; by = nby;
     }
 }
 
