@@ -478,7 +478,7 @@ struct RowDemodParams {
     int H, ncp;
     int nc[2];
     int kc0[2];
-    int x_ref;           // anchor column of the row unwrap: W / 2 (the kernels compile it in as L / 2)
+    int x_ref;
     int unwrap;
     int* frameflag;      // [F] or null: set to 1 for frames with |phi| > pi/2 somewhere (the only frames that can
                          // hold a 2*pi jump, let alone a residue: unwrap "auto" looks no further at the others)
@@ -497,7 +497,6 @@ struct RowDemod {
     static constexpr int SYNC_THREADS = (L / 16 >= 32 && G > 1 && G <= 15) ? L / 16 : 0;   // per-group named barriers
     static constexpr int MIN_BLOCKS = ((G * L / 16) <= 128 ? 4 : ((G * L / 16) <= 256 ? 2 : 1));
     static constexpr int TPF = GL::TPF, THREADS = GL::THREADS, PHASES = 13;
-    static constexpr int X_REF = L / 2;      // anchor column of the row unwrap (Params::x_ref must say the same)
     using TW = SmemTwiddles<FF, THREADS>;
     // per group: two exchange buffers (one per carrier; the second doubles as the jump-scan
     // array), chunk totals, chunk offsets, flag, and (pruned path) the staging slots of the
@@ -527,14 +526,12 @@ struct RowDemod {
         return reinterpret_cast<cf*>(gbase + GL::GROUP_STRIDE * sizeof(cf) + AUX_INTS * sizeof(int));
     }
     FCD_HD static void stage_band(const Params& p, int f, int y, int t, cf* band) {
-        // one 64-bit row address per carrier, 32-bit offsets inside the row
-        const cf* __restrict__ row0 = p.w2 + ((long long)f * 2 * p.H + y) * p.ncp;
-        const cf* __restrict__ row1 = row0 + (long long)p.H * p.ncp;
         FCD_UNROLL
         for (int q = 0; q < 4; ++q) {
             const int i = q >> 1;
             const int c = band_col(p, i, t, q & 1);
-            if (c < p.nc[i]) async_copy8(band + q * TPF + t, (i == 0 ? row0 : row1) + c);
+            if (c < p.nc[i])
+                async_copy8(band + q * TPF + t, p.w2 + (((long long)f * 2 + i) * p.H + y) * p.ncp + c);
         }
     }
 
@@ -674,8 +671,12 @@ struct RowDemod {
             for (int m = 0; m < 16; ++m) st.v[m] = mk<float>(ph0[m], ph1[m]);
 #endif
             // wrapped phase at the anchor column links the rows (RowLink)
-            if (t == X_REF % TPF) {            // the anchor column is a compile-time slot of one thread
-                const cf a = st.v[X_REF / TPF];
+            if (t == (p.x_ref % TPF)) {
+                const int mr = p.x_ref / TPF;
+                cf a = mk<float>(0.f, 0.f);
+                FCD_UNROLL
+                for (int mm = 0; mm < 16; ++mm)
+                    if (mm == mr) a = st.v[mm];
                 p.colphase[((long long)f * 2 + 0) * p.H + y] = a.x;
                 p.colphase[((long long)f * 2 + 1) * p.H + y] = a.y;
             }
@@ -712,8 +713,8 @@ struct RowDemod {
             int2s o; o.a = a; o.b = b;
             off[t] = o;
         } else if constexpr (PH == 8) {
-            const int2s cr = sj[fft_pos(X_REF)];
-            const int2s orf = off[X_REF >> 4];
+            const int2s cr = sj[fft_pos(p.x_ref)];
+            const int2s orf = off[p.x_ref >> 4];
             const int ra = cr.a + orf.a, rb = cr.b + orf.b;
             FCD_UNROLL
             for (int m = 0; m < 16; ++m) {

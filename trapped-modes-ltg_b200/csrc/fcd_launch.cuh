@@ -174,18 +174,23 @@ __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) fcd_kernel(const __
         t1 = (int)((long long)(blockIdx.x + 1) * ntiles / gridDim.x);
         step = 1;
     }
-    // tile -> (bx, by) = (tile % gx, tile / gx), kept incrementally: two divisions per block instead of four per
-    // tile (the issue-bound kernels spent 4 % of their instructions on them, SASS of round 2)
+    // tile -> (bx, by) = (tile % gx, tile / gx), kept incrementally: two divisions per block instead of two per tile.
+    // Only (bx, by) live across a tile, as before: the next tile's coordinates are formed twice (for the prefetch
+    // link, which dies early, and at the loop end) rather than carried through a kernel that sits at its register cap.
     if (t0 >= t1) return;
     int bx = t0 % gx, by = t0 / gx;
-    const int sx = step % gx, sy = step / gx;
+    int sx = 1, sy = 0;                              // BLOCKED_TILES: step == 1
+    if (!K::BLOCKED_TILES) { sx = step % gx; sy = step / gx; }
     for (int tile = t0; tile < t1; tile += step) {
-        int nbx = bx + sx, nby = by + sy;
-        if (nbx >= gx) { nbx -= gx; ++nby; }
-        if constexpr (K::PIPELINED) st.link = TileLink{nbx, nby, tile + step < t1, tile == t0};
+        if constexpr (K::PIPELINED) {
+            int nbx = bx + sx, nby = by + sy;
+            if (nbx >= gx) { nbx -= gx; ++nby; }
+            st.link = TileLink{nbx, nby, tile + step < t1, tile == t0};
+        }
         run_phases<K, 0>(p, bx, by, fcd_smem, st);
         phase_barrier<K>();
-        bx = nbx; by = nby;
+        bx += sx; by += sy;
+        if (bx >= gx) { bx -= gx; ++by; }
     }
 }
 
