@@ -113,3 +113,56 @@ def test_known_answers_from_reference_fixtures():
     assert [p.tolist() for p in peaks] == [[564, 566], [458, 564]]
     assert [p.tolist() for p in o.find_peaks(load("reference_2.png"))] == [[443, 590], [434, 443]]
     assert [p.tolist() for p in o.find_peaks(load("prueba1_20250317_122608_C1S0001000001.tif"))] == [[557, 558], [466, 557]]
+
+
+@pytest.mark.parametrize("shape,seed", [((24, 37), 1), ((40, 32), 2), ((33, 33), 3)])
+def test_unwrap_oracle_is_integration_along_the_minimum_spanning_tree(shape, seed):
+    """Second, independent statement of what oracle/unwrap_herraez.c computes (and of what the CUDA unwrapper relies
+    on, csrc/fcd_unwrap.cuh): merging neighbour pairs in ascending order of summed reliabilities and skipping pairs
+    inside a group is Kruskal's algorithm, so the unwrapped map is the integral of the wrapped differences along the
+    minimum spanning tree under the strict order (cost, edge index: horizontal edges before vertical, raster order).
+    Here the tree comes from scipy (edge weights = ranks in that order, hence unique) and the integration from a
+    breadth-first walk; reliabilities are recomputed in numpy with the oracle's border filler."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import breadth_first_order, minimum_spanning_tree
+    rng = np.random.default_rng(seed)
+    H, W = shape
+    y, x = np.mgrid[0:H, 0:W]
+    smooth = 7.0 * np.exp(-((y - H / 2) ** 2 + (x - W / 3) ** 2) / (2 * (H / 4) ** 2)) + 0.11 * x
+    w = np.angle(np.exp(1j * (smooth + 1.2 * rng.standard_normal(shape))))
+    assert o.count_residues(w) > 10
+    got = o.unwrap_phase(w)
+
+    def wrap(d):
+        return np.where(d > np.pi, d - 2 * np.pi, np.where(d < -np.pi, d + 2 * np.pi, d))
+
+    # reliabilities: wrapped second differences inside, the oracle's deterministic filler on the border
+    n = H * W
+    lcg, rel = 0x9E3779B97F4A7C15, np.empty(n)
+    for i in range(n):
+        lcg = (lcg * 6364136223846793005 + 1442695040888963407) % (1 << 64)
+        rel[i] = 9999999.0 + (lcg >> 11) / 9007199254740992.0
+    rel = rel.reshape(shape)
+    c = w[1:-1, 1:-1]
+    h = wrap(w[1:-1, :-2] - c) - wrap(c - w[1:-1, 2:])
+    v = wrap(w[:-2, 1:-1] - c) - wrap(c - w[2:, 1:-1])
+    d1 = wrap(w[:-2, :-2] - c) - wrap(c - w[2:, 2:])
+    d2 = wrap(w[:-2, 2:] - c) - wrap(c - w[2:, :-2])
+    rel[1:-1, 1:-1] = h * h + v * v + d1 * d1 + d2 * d2
+    idx = np.arange(n).reshape(shape)
+    p = np.concatenate([idx[:, :-1].ravel(), idx[:-1, :].ravel()])          # horizontal edges first, raster order
+    q = np.concatenate([idx[:, 1:].ravel(), idx[1:, :].ravel()])
+    cost = rel.ravel()[p] + rel.ravel()[q]
+    rank = np.empty(len(p)); rank[np.argsort(cost, kind="stable")] = np.arange(1, len(p) + 1)
+    tree = minimum_spanning_tree(coo_matrix((rank, (p, q)), shape=(n, n)).tocsr())
+    sym = tree + tree.T
+    order, pred = breadth_first_order(sym, 0, directed=False)
+    flat, k = w.ravel(), np.zeros(n, dtype=np.int64)
+    for node in order[1:]:
+        par = pred[node]
+        d = flat[par] - flat[node]                                           # continue the parent's branch
+        k[node] = k[par] + (1 if d > np.pi else (-1 if d < -np.pi else 0))
+    want = flat + 2 * np.pi * k
+    diff = (got.ravel() - want) / (2 * np.pi)
+    assert np.abs(diff - np.round(diff)).max() < 1e-9
+    assert np.unique(np.round(diff)).size == 1                               # equal up to one global 2*pi*k
