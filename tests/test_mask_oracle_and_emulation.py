@@ -146,3 +146,70 @@ def test_emulated_box_filter_is_scipys_uniform_filter(size):
         want = uniform_filter(imgs[k], size)
         assert want.dtype == np.float32
         assert np.array_equal(out[k].view(np.uint32), want.view(np.uint32)), (size, k)
+
+
+# ---- warp-level model of LabelInit's device path (csrc/fcd_mask.cuh) --------------------------------------------
+# The CPU emulation runs LabelInit's sequential branch; its device branch (ballots, 16 mask bytes per lane gathered
+# into bitmap words by a multiply and one shuffle, ragged trips for narrow images) is mirrored here lane by lane so
+# that its bit logic is checked for every supported width, including the 64- and 128-pixel rows no GPU test covers.
+def _ballot(pred):  # list of 32 bools -> word
+    w=0
+    for l,p in enumerate(pred):
+        if p: w|=1<<l
+    return w
+def _vcmpeq4_zero(w):
+    r=0
+    for k in range(4):
+        if ((w>>(8*k))&0xff)==0: r|=0xff<<(8*k)
+    return r
+def _nib(w): return ((((_vcmpeq4_zero(w)&0x01010101)*0x01020408)&0xffffffff)>>24)&15
+def _model(mask_row=None, smooth_row=None, thr=0.0, W=64, r=3):
+    """returns (bits words, dict of L writes {col: value})"""
+    L={}; bits=[None]*(W//32); carry=[0]
+    def emit(b,c0):
+        starts=b & ~(((b<<1)&0xffffffff)|carry[0])
+        for lane in range(32):
+            if (starts>>lane)&1: L[c0+lane]=r*W+c0+lane
+        carry[0]=b>>31
+    if smooth_row is not None:
+        for c0 in range(0,W,128):
+            v=[[ (smooth_row[c0+32*q+lane] if c0+32*q<W else thr) for lane in range(32)] for q in range(4)]
+            mine=[0]*32
+            for q in range(4):
+                if c0+32*q<W:
+                    b=_ballot([v[q][lane]<thr for lane in range(32)])
+                    emit(b,c0+32*q)
+                    mine[q]=b
+            for lane in range(4):
+                if c0+32*lane<W: bits[(c0>>5)+lane]=mine[lane]
+    else:
+        for c0 in range(0,W,512):
+            vs=[]
+            for lane in range(32):
+                inn=c0+16*lane<W
+                if inn:
+                    by=mask_row[c0+16*lane:c0+16*lane+16]
+                    m=[int.from_bytes(bytes(by[4*k:4*k+4]),'little') for k in range(4)]
+                else: m=[0x01010101]*4
+                v=_nib(m[0])|(_nib(m[1])<<4)|(_nib(m[2])<<8)|(_nib(m[3])<<12)
+                v=(v<<(16*(lane&1)))&0xffffffff
+                vs.append(v)
+            vs2=[vs[l]|vs[l^1] for l in range(32)]
+            for q in range(16):
+                b=vs2[2*q]
+                if c0+32*q<W: emit(b,c0+32*q)
+            for lane in range(32):
+                if not (lane&1) and c0+16*lane<W: bits[(c0>>5)+(lane>>1)]=vs2[lane]
+    return bits,L
+
+@pytest.mark.parametrize("W", [64, 128, 256, 512, 1024, 2048])
+def test_label_init_device_path_bit_logic(W):
+    rng = np.random.default_rng(W)
+    for trial in range(20):
+        fg = rng.random(W) < rng.choice([0.0, 0.1, 0.5, 0.9, 1.0])
+        want_bits = [sum(int(fg[32 * w + i]) << i for i in range(32)) for w in range(W // 32)]
+        want_starts = {c: 3 * W + c for c in range(W) if fg[c] and not (c > 0 and fg[c - 1])}
+        mask = np.where(fg, 0, rng.integers(1, 256, W)).astype(np.uint8)                   # mode 1: foreground = !mask
+        assert _model(mask_row=mask, W=W) == (want_bits, want_starts)
+        smooth = np.where(fg, 0.2, 0.8).astype(np.float32)                                  # mode 0: smooth < threshold
+        assert _model(smooth_row=smooth, thr=0.5, W=W) == (want_bits, want_starts)
