@@ -213,3 +213,49 @@ def test_label_init_device_path_bit_logic(W):
         assert _model(mask_row=mask, W=W) == (want_bits, want_starts)
         smooth = np.where(fg, 0.2, 0.8).astype(np.float32)                                  # mode 0: smooth < threshold
         assert _model(smooth_row=smooth, thr=0.5, W=W) == (want_bits, want_starts)
+
+
+def _box_rows_warp_model(a, size):
+    """One lane's row through BoxRowsWarp's device path (csrc/fcd_mask.cuh): ring of three 32-column tiles, tile k + 2
+    parked while tile k is filtered, interior tiles without the reflection lookup.  The emulation runs the kernel's
+    sequential branch; this mirrors the tile bookkeeping of the device branch for every window the kernel takes."""
+    n = len(a); s1 = size // 2; s2 = size - s1 - 1; ntiles = n // 32
+    T = [None, None, None]
+
+    def at(j):                                   # 'reflect', then the ring
+        if j < 0: j = -j - 1
+        if j >= n: j = 2 * n - 1 - j
+        return float(T[(j >> 5) % 3][j & 31])
+
+    T[0] = a[0:32].copy()
+    if ntiles > 1: T[1] = a[32:64].copy()
+    tmp = 0.0
+    for l in range(size): tmp += at(l - s1)
+    out, slot, d = np.empty(n, np.float32), 0, float(size)
+    for k in range(ntiles):
+        more = k + 2 < ntiles
+        parked = a[32 * (k + 2):32 * (k + 3)].copy() if more else None
+        if 0 < k < ntiles - 1:
+            tc, tn, tp = T[slot], T[0 if slot == 2 else slot + 1], T[2 if slot == 0 else slot - 1]
+            for cc in range(32):
+                jn, jo = cc + s2, cc - 1 - s1
+                tmp += (float(tc[jn]) if jn < 32 else float(tn[jn - 32])) - (float(tc[jo]) if jo >= 0 else float(tp[jo + 32]))
+                out[32 * k + cc] = np.float32(tmp / d)
+        else:
+            for cc in range(32):
+                l = 32 * k + cc
+                if l > 0: tmp += at(l + s2) - at(l - 1 - s1)
+                out[l] = np.float32(tmp / d)
+        if more: T[2 if slot == 0 else slot - 1] = parked
+        slot = 0 if slot == 2 else slot + 1
+    return out
+
+
+@pytest.mark.parametrize("n", [64, 128, 256])
+def test_box_rows_warp_tile_bookkeeping(n):
+    from scipy.ndimage import uniform_filter1d
+    rng = np.random.default_rng(n)
+    for size in range(1, 33):
+        a = rng.integers(0, 4096, n).astype(np.float32) + rng.random(n).astype(np.float32)
+        want = uniform_filter1d(a, size)
+        assert np.array_equal(_box_rows_warp_model(a, size).view(np.uint32), want.view(np.uint32)), size
