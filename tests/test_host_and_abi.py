@@ -210,3 +210,44 @@ def test_mask_bytes_reinterprets_instead_of_copying():
     assert nb.dtype == torch.uint8 and nb.tolist() == [[1, 0]]
     t = torch.ones((4, 6), dtype=torch.bool)[:, ::2]                                    # non-contiguous view
     assert e._mask_bytes(t, torch.device("cpu")).is_contiguous()
+
+
+def test_launcher_tile_coordinates_model():
+    """csrc/fcd_launch.cuh keeps (bx, by) = (tile % gx, tile / gx) incrementally (no division per tile).  Model of that
+    loop for both tile orders: every block must visit exactly its tiles with the right coordinates and hand the right
+    next-tile link to the kernels that prefetch."""
+    def block_tiles(blk, grid, gx, ntiles, blocked):
+        t0, t1, step = blk, ntiles, grid
+        if blocked:
+            t0, t1, step = blk * ntiles // grid, (blk + 1) * ntiles // grid, 1
+        if t0 >= t1:
+            return []
+        bx, by = t0 % gx, t0 // gx
+        sx, sy = (1, 0) if blocked else (step % gx, step // gx)
+        seen, tile = [], t0
+        while tile < t1:
+            nbx, nby = bx + sx, by + sy
+            if nbx >= gx:
+                nbx -= gx; nby += 1
+            seen.append((tile, bx, by, nbx, nby, tile + step < t1, tile == t0))
+            bx += sx; by += sy
+            if bx >= gx:
+                bx -= gx; by += 1
+            tile += step
+        return seen
+
+    for gx, gy, grid in [(1, 1, 1), (1, 7, 3), (5, 1, 2), (128, 512, 148), (3, 1025, 148), (1000, 2, 296), (7, 11, 77), (2, 3, 6)]:
+        ntiles = gx * gy
+        grid = min(grid, ntiles)
+        for blocked in (False, True):
+            visited = []
+            for blk in range(grid):
+                tiles = block_tiles(blk, grid, gx, ntiles, blocked)
+                step = 1 if blocked else grid
+                for i, (tile, bx, by, nbx, nby, has_next, first) in enumerate(tiles):
+                    assert (bx, by) == (tile % gx, tile // gx)
+                    assert first == (i == 0) and has_next == (i + 1 < len(tiles))
+                    if has_next:
+                        assert (nbx, nby) == ((tile + step) % gx, (tile + step) // gx)
+                    visited.append(tile)
+            assert sorted(visited) == list(range(ntiles))
