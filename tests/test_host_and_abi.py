@@ -251,3 +251,32 @@ def test_launcher_tile_coordinates_model():
                         assert (nbx, nby) == ((tile + step) % gx, (tile + step) // gx)
                     visited.append(tile)
             assert sorted(visited) == list(range(ntiles))
+
+
+def test_folder_mask_preview_dialogue(tmp_path, monkeypatch):
+    """analyze.folder(show_mask=True) (pydata/analyze.py:193-217): the eleventh frame (or the last one) is previewed,
+    "n" asks for a new `smoothed`, a non-integer keeps the previous one, "Y" accepts; without `smoothed` it is a
+    ValueError.  matplotlib, the image decode and the device mask are stubbed: this is the dialogue only."""
+    import types
+    from pydata.analyze import analyze
+    events = []
+    plt = types.ModuleType("matplotlib.pyplot")
+    plt.pause = lambda s: events.append(("pause", s))
+    plt.close = lambda what: events.append(("close", what))
+    mpl = types.ModuleType("matplotlib"); mpl.pyplot = plt
+    monkeypatch.setitem(sys.modules, "matplotlib", mpl)
+    monkeypatch.setitem(sys.modules, "matplotlib.pyplot", plt)
+    monkeypatch.setattr(analyze, "load_image", classmethod(lambda cls, path: events.append(("load", os.path.basename(path))) or np.zeros((4, 4), np.float32)))
+    monkeypatch.setattr(analyze, "mask", classmethod(lambda cls, image, smoothed=14, show_mask=False, find_center=False:
+                                                     events.append(("mask", smoothed, show_mask))))
+    answers = iter(["n", "21", "maybe", "n", "x1", "Y"])
+    names = [f"f{i:02d}.tif" for i in range(14)]
+    got = analyze._preview_mask(str(tmp_path), names, 15, ask=lambda prompt: next(answers))
+    assert got == 21
+    assert events[0] == ("load", "f10.tif")
+    assert [e[1] for e in events if e[0] == "mask"] == [15, 21, 21, 21] and all(e[2] for e in events if e[0] == "mask")
+    assert events.count(("pause", 8)) == 4 and events.count(("close", "all")) == 4
+    events.clear()
+    assert analyze._preview_mask(str(tmp_path), names[:3], 9, ask=lambda prompt: "Y") == 9 and events[0] == ("load", "f02.tif")
+    with pytest.raises(ValueError):
+        analyze.folder("ref.tif", str(tmp_path), None, 1.0, smoothed=None, show_mask=True)

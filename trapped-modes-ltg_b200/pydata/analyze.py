@@ -75,12 +75,13 @@ class analyze:
         pydata/analyze.py:141-286, same file selection, resume rule and output formats.  Frames are
         decoded on the host, then masked (analyze.mask / center), demodulated and integrated on
         the device ``batch`` at a time with the per-reference work done once; integer camera
-        frames travel as integers and are widened in the first kernel.  The polar output
-        (cv2.fitEllipse + warp) and the interactive mask preview are not part of this mirror."""
+        frames travel as integers and are widened in the first kernel.  ``show_mask`` runs the reference's
+        interactive preview first (``_preview_mask``); the polar output (cv2.fitEllipse + warp) is not part of
+        this mirror."""
         if polar:
             raise NotImplementedError("polar maps (analyze.py:236-243,264-275) are outside the mirrored path")
-        if show_mask:
-            raise NotImplementedError("the interactive mask preview (analyze.py:193-215) is outside the mirrored path")
+        if show_mask and not smoothed:
+            raise ValueError("If show_mask == True, expect smoothed too")          # analyze.py:216-217
         import cv2
         reference = cls.load_image(reference_path)
         file_list = sorted(os.listdir(displaced_dir))
@@ -96,6 +97,8 @@ class analyze:
             with open(centers_path, "r") as f:
                 lines = f.readlines()
             start_index = max(start_index, len(lines))
+            if show_mask:
+                smoothed = cls._preview_mask(displaced_dir, tif_list, smoothed)
         todo = list(enumerate(tif_list))[start_index:]
         if not todo:
             return
@@ -128,6 +131,26 @@ class analyze:
                 if not calibration_saved:
                     np.save(os.path.join(output_dir, 'calibration_factor.npy'), np.array([calibration_factor]))
                     calibration_saved = True
+
+    @classmethod
+    def _preview_mask(cls, displaced_dir, tif_list, smoothed, ask=input):
+        """The interactive preview of ``folder(show_mask=True)``: show the mask of the eleventh frame (or the last
+        one), ask, and let the user try another ``smoothed`` until the answer is "Y".  Returns the accepted value.
+        Reference: pydata/analyze.py:193-215 (same prompts, same 8 s pause)."""
+        import matplotlib.pyplot as plt
+        displaced_image = cls.load_image(os.path.join(displaced_dir, tif_list[min(10, len(tif_list) - 1)]))
+        while True:
+            cls.mask(displaced_image, smoothed=smoothed, show_mask=True)
+            plt.pause(8)
+            plt.close("all")
+            message = ask("Continue with this mask? [Y,n]: ")
+            if message == "Y":
+                return smoothed
+            if message == "n":
+                try:
+                    smoothed = int(ask("Enter new smoothed value (int): "))
+                except ValueError:
+                    print("Invalid input, keeping previous smoothed.")
 
     @classmethod
     def block_split(cls, map_folder, t_limit=None, num_blocks=64, block_index=0):
